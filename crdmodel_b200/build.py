@@ -1,0 +1,79 @@
+"""Build libcrd_b200.so (sm_100a CUDA kernels + C ABI + host integrator) in-tree with nvcc.
+
+    python -m crdmodel_b200.build        # or crdmodel_b200.build.build()
+
+nvcc cross-compiles without a GPU.  The library lands in crdmodel_b200/lib/ (git-ignored, travels
+to the GPU box with the snapshot).
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_DIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIB_DIR, "libcrd_b200.so")
+
+CUDA_SOURCES = ["csrc/crd_ctx.cu", "csrc/crd_rhs.cu", "csrc/crd_nvector.cu"]
+HOST_SOURCES = ["host/crd_ark.cpp", "host/crd_nvector_generic.c"]
+HEADERS = ["csrc/crd_common.cuh", "csrc/crd_grid.cuh", "../include/crd_b200.h", "../include/crd_ark.h",
+           "../include/crd_sundials_compat.h"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC,-ffp-contract=off", "-Xlinker", "-Bsymbolic", "-shared"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(HERE, s)) > t for s in CUDA_SOURCES + HOST_SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "csrc"),
+                                    "-o", LIB] + [os.path.join(HERE, s) for s in CUDA_SOURCES + HOST_SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+def build_drivers(verbose=False):
+    """The four host executables (same names as the reference's CMake targets, CMakeLists.txt:37-50)."""
+    src = os.path.join(HERE, "host", "crd_driver.cpp")
+    if not os.path.exists(src):
+        return []
+    out = []
+    os.makedirs(os.path.join(ROOT, "bin"), exist_ok=True)
+    for name, model in (("FHNmodel_torus", 0), ("GoldbeterModel_torus", 1), ("FHNmodel_flat", 2), ("GoldbeterModel_flat", 3)):
+        exe = os.path.join(ROOT, "bin", name)
+        if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
+            out.append(exe)
+            continue
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-DCRD_DRIVER_MODEL=%d" % model,
+               "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "host"), src, "-o", exe,
+               "-L" + LIB_DIR, "-lcrd_b200", "-Wl,-rpath,$ORIGIN/../crdmodel_b200/lib", "-lpthread", "-lrt"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+        out.append(exe)
+    return out
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    build_drivers(verbose=True)
+    print(LIB)

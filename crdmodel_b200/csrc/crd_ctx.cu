@@ -1,0 +1,189 @@
+// crd_ctx.cu — device context, memory helpers, timers, synthetic-state generator.
+#include "crd_common.cuh"
+
+namespace crd {
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+}  // namespace crd
+
+using namespace crd;
+
+extern "C" {
+
+const char *crd_last_error(void) { return g_err; }
+
+int crd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+crd_ctx *crd_ctx_create(int device, void *stream) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s); libcrd_b200 has no CPU path", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (device < 0 || device >= n) { set_error("device %d out of range (have %d)", device, n); return nullptr; }
+  CRD_CUDA_NULL(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CRD_CUDA_NULL(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libcrd_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    return nullptr;
+  }
+  crd_ctx *c = new crd_ctx;
+  c->device = device;
+  if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+  else { CRD_CUDA_NULL(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  CRD_CUDA_NULL(cudaMalloc(&c->red_partial, sizeof(double) * kRedSlots * kRedBlocks));
+  CRD_CUDA_NULL(cudaMalloc(&c->red_ticket, sizeof(unsigned int)));
+  CRD_CUDA_NULL(cudaMemset(c->red_ticket, 0, sizeof(unsigned int)));
+  CRD_CUDA_NULL(cudaHostAlloc(&c->red_result_host, sizeof(double) * kRedSlots, cudaHostAllocMapped));
+  CRD_CUDA_NULL(cudaHostGetDevicePointer(&c->red_result_dev, c->red_result_host, 0));
+  CRD_CUDA_NULL(cudaHostAlloc(&c->err_host, sizeof(int), cudaHostAllocMapped));
+  *c->err_host = 0;
+  CRD_CUDA_NULL(cudaHostGetDevicePointer(&c->err_dev, c->err_host, 0));
+  CRD_CUDA_NULL(cudaEventCreate(&c->ev0));
+  CRD_CUDA_NULL(cudaEventCreate(&c->ev1));
+  return c;
+}
+
+void crd_ctx_destroy(crd_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  cudaFree(c->red_partial);
+  cudaFree(c->red_ticket);
+  cudaFreeHost(c->red_result_host);
+  cudaFreeHost(c->err_host);
+  if (c->flush_buf) cudaFree(c->flush_buf);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  delete c;
+}
+
+int crd_ctx_set_comm(crd_ctx *c, int rank, int nranks, crd_allreduce_fn fn, void *user) {
+  if (!c || nranks < 1 || rank < 0 || rank >= nranks) { set_error("crd_ctx_set_comm: bad arguments"); return -1; }
+  if (nranks > 1 && !fn) { set_error("crd_ctx_set_comm: nranks > 1 needs an allreduce function"); return -1; }
+  c->rank = rank; c->nranks = nranks; c->allreduce = fn; c->allreduce_user = user;
+  return 0;
+}
+
+void *crd_ctx_stream(crd_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int crd_ctx_device(crd_ctx *c) { return c ? c->device : -1; }
+int64_t crd_ctx_launch_count(crd_ctx *c) { return c ? c->launches : 0; }
+
+int crd_ctx_sync(crd_ctx *c) {
+  if (use(c)) return -1;
+  CRD_CUDA(cudaStreamSynchronize(c->stream));
+  if (*c->err_host != 0) { set_error("device-side error %d (halo wait timed out)", *c->err_host); return -2; }
+  return 0;
+}
+
+int crd_timer_start(crd_ctx *c) {
+  if (use(c)) return -1;
+  CRD_CUDA(cudaEventRecord(c->ev0, c->stream));
+  return 0;
+}
+int crd_timer_stop(crd_ctx *c, double *ms) {
+  if (use(c)) return -1;
+  CRD_CUDA(cudaEventRecord(c->ev1, c->stream));
+  CRD_CUDA(cudaEventSynchronize(c->ev1));
+  float f = 0;
+  CRD_CUDA(cudaEventElapsedTime(&f, c->ev0, c->ev1));
+  *ms = f;
+  return 0;
+}
+
+void *crd_malloc(crd_ctx *c, size_t bytes) {
+  if (use(c)) return nullptr;
+  void *p = nullptr;
+  CRD_CUDA_NULL(cudaMalloc(&p, bytes ? bytes : 16));
+  return p;
+}
+int crd_free(crd_ctx *c, void *p) {
+  if (use(c)) return -1;
+  CRD_CUDA(cudaFree(p));
+  return 0;
+}
+void *crd_malloc_host(size_t bytes) {
+  void *p = nullptr;
+  CRD_CUDA_NULL(cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault));
+  return p;
+}
+int crd_free_host(void *p) { CRD_CUDA(cudaFreeHost(p)); return 0; }
+
+int crd_memcpy_h2d(crd_ctx *c, void *dst, const void *src, size_t bytes) {
+  if (use(c)) return -1;
+  CRD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  CRD_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int crd_memcpy_d2h(crd_ctx *c, void *dst, const void *src, size_t bytes) {
+  if (use(c)) return -1;
+  CRD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CRD_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int crd_memset_zero(crd_ctx *c, void *dst, size_t bytes) {
+  if (use(c)) return -1;
+  CRD_CUDA(cudaMemsetAsync(dst, 0, bytes, c->stream));
+  return 0;
+}
+
+int crd_flush_l2(crd_ctx *c) {
+  if (use(c)) return -1;
+  if (!c->flush_buf) {
+    c->flush_bytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
+    CRD_CUDA(cudaMalloc(&c->flush_buf, c->flush_bytes));
+  }
+  CRD_CUDA(cudaMemsetAsync(c->flush_buf, 0x5a, c->flush_bytes, c->stream));
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- synthetic state: jump-ahead LCG, one thread per 32-element run --------------------------------
+namespace {
+constexpr unsigned long long LCG_A = 6364136223846793005ULL, LCG_C = 1442695040888963407ULL;
+constexpr int kRun = 32;
+
+__global__ void __launch_bounds__(256) fill_synthetic_kernel(int fhn, unsigned long long seed, long long first, long long n,
+                                                             double *__restrict__ out) {
+  long long run = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long e0 = run * kRun;
+  if (e0 >= n) return;
+  // affine map composed (first + e0) times
+  unsigned long long accA = 1ULL, accC = 0ULL, curA = LCG_A, curC = LCG_C;
+  for (unsigned long long k = (unsigned long long)(first + e0); k; k >>= 1) {
+    if (k & 1ULL) { accA = accA * curA; accC = accC * curA + curC; }
+    curC = curC * curA + curC;
+    curA = curA * curA;
+  }
+  unsigned long long s = accA * seed + accC;
+  long long e1 = e0 + kRun < n ? e0 + kRun : n;
+  for (long long e = e0; e < e1; ++e) {
+    s = s * LCG_A + LCG_C;
+    double u = __dmul_rn((double)(s >> 11), 1.0 / 9007199254740992.0);
+    out[e] = fhn ? __dsub_rn(__dmul_rn(4.0, u), 2.0) : __dadd_rn(__dmul_rn(1.5, u), 0.1);
+  }
+}
+}  // namespace
+
+extern "C" int crd_fill_synthetic(crd_ctx *c, int model, uint64_t seed, int64_t first_elem, int64_t n, double *out_dev) {
+  if (use(c)) return -1;
+  if (n <= 0) return 0;
+  int fhn = (model == CRD_FHN_TORUS || model == CRD_FHN_FLAT);
+  long long runs = (n + kRun - 1) / kRun;
+  unsigned int blocks = (unsigned int)((runs + 255) / 256);
+  fill_synthetic_kernel<<<blocks, 256, 0, c->stream>>>(fhn, seed, first_elem, n, out_dev);
+  return check_launch(c, "fill_synthetic_kernel");
+}

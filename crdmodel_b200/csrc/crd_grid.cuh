@@ -1,0 +1,77 @@
+// crd_grid.cuh — the grid descriptor (device-side equivalent of the reference's UserData,
+// src/FHNmodel_torus.cpp:97-122) and the kernel argument block of the fused RHS.
+#pragma once
+#include "crd_common.cuh"
+
+namespace crd {
+
+// Scalars the RHS kernels need; filled once per grid on the host with the reference's own expressions
+// so that the EXACT kernels reproduce its rounding.
+struct RhsConst {
+  double Diff;
+  // torus, exact: T = Diff*(a*(...))/den
+  double inv_rr;   // 1/(r*r)
+  double twodx;    // 2*dx
+  double dxdx;     // dx*dx
+  double dydy;     // dy*dy
+  // torus, fast: folded
+  double c2;       // Diff*inv_rr/dxdx
+  // flat (FHNmodel_flat.cpp:489-491)
+  double cu1, cu2, cu3;
+  // Goldbeter constants evaluated by the host libm (GoldbeterModel_torus.cpp:694-695)
+  double k2n;      // pow(K2, n) = 1
+  double krm;      // pow(KR, m) = 4
+  double kap;      // pow(KA, p) = 0.6561...
+};
+
+struct RhsArgs {
+  const double *y;
+  double *ydot;
+  const double *south;   // u of global row js-1:  south[i*south_stride]
+  const double *north;   // u of global row je+1:  north[i*north_stride]
+  long long south_stride, north_stride;
+  const double *cth;     // [nx][2]: exact (a1, a3) | fast (c1, c3); unused for flat
+  const double *brow;    // [nyl]: FHN b(phi) | Goldbeter v0 + v1*b(phi)
+  long long nx, nyl;
+  int freeze_south;      // t < tBoundary && js == 0       (:649)
+  int freeze_north;      // t < tBoundary && je == ny-1    (:643)
+  int react;             // 0 only for Goldbeter with justDiffusion (:668)
+  RhsConst k;
+};
+
+// ghost block, one per grid, cudaMalloc'd so it can be exported with cudaIpcGetMemHandle:
+//   double ghost[2 parity][2 side][nx]     side 0 = south (row js-1), side 1 = north (row je+1)
+//   unsigned long long flag[2 side]        epoch of the last complete push, 128 B apart
+struct HaloLayout {
+  long long nx;
+  __host__ __device__ size_t ghost_off(int parity, int side) const { return (size_t)(parity * 2 + side) * (size_t)nx * sizeof(double); }
+  __host__ __device__ size_t flag_off(int side) const { return (size_t)4 * (size_t)nx * sizeof(double) + 128 + (size_t)side * 128; }
+  __host__ __device__ size_t bytes() const { return flag_off(1) + 128; }
+};
+
+}  // namespace crd
+
+struct crd_grid {
+  crd_ctx *ctx = nullptr;
+  crd_params p{};
+  long long nx = 0, ny = 0, js = 0, je = 0, nyl = 0;
+  double dx = 0, dy = 0, R = 0, r = 0, xmin = 0, xmax = 0, ymin = 0, ymax = 0;
+  crd::RhsConst k{};
+  double *cth = nullptr;
+  double *brow = nullptr;
+  // halo ring
+  char *halo_local = nullptr;
+  char *halo_prev = nullptr, *halo_next = nullptr;  // peer-mapped (or local) ghost blocks of the neighbours
+  bool prev_ipc = false, next_ipc = false;
+  bool connected = false;
+  unsigned long long *push_ticket = nullptr;
+  unsigned long long epoch = 0;      // epoch of the last post
+  unsigned long long computed = 0;   // epoch of the last compute
+  int64_t rhs_count = 0;
+  int variant = 0;
+  // crd_rhs_host staging
+  double *stage_y = nullptr, *stage_ydot = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t *ev_in = nullptr, *ev_k = nullptr;
+  int n_chunks = 0;
+};

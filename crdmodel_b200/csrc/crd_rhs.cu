@@ -1,0 +1,595 @@
+// crd_rhs.cu — the fused stencil + reaction right-hand side, its grid descriptor and the halo ring.
+//
+// Reference being replaced: f() of the four programs
+//   src/FHNmodel_torus.cpp:504-667, src/GoldbeterModel_torus.cpp:547-724,
+//   src/FHNmodel_flat.cpp:469-616,  src/GoldbeterModel_flat.cpp:515-689
+// which make three sweeps over memory per evaluation (N_VConst, stencil, reaction) and re-evaluate
+// sin/cos per point.  Here: ONE pass, 16 B read + 16 B written per grid point, metric coefficients
+// from a per-theta table computed once on the host with the reference's own expressions.
+//
+// Kernel shape (HBM-bound, no tensor cores: nothing here is a contraction): every thread owns one
+// theta column of RY consecutive phi rows.  It issues all its loads first (RY 16-byte centre loads,
+// the east/west u values, one u above and one below), then computes RY points and stores RY 16-byte
+// results, so each state row is fetched from HBM once and the row above/below comes from L2/L1.
+#include <cmath>
+#include <vector>
+
+#include "crd_grid.cuh"
+
+using namespace crd;
+
+namespace {
+
+constexpr double kEps = 0.36;   // EPSILON, FHNmodel_torus.cpp:68
+constexpr double kPI = 3.1415926535897932;  // FHNmodel_torus.cpp:63
+// Goldbeter constants, GoldbeterModel_torus.cpp:67-78
+constexpr double G_v0 = 1.0, G_k = 10.0, G_kf = 1.0, G_v1 = 7.3, G_VM2 = 65.0, G_VM3 = 500.0;
+constexpr double G_K2 = 1.0, G_KR = 2.0, G_KA = 0.9, G_m = 2.0, G_n = 2.0, G_p = 4.0;
+
+__host__ __device__ constexpr bool is_torus(int model) { return model == CRD_FHN_TORUS || model == CRD_GOLDBETER_TORUS; }
+__host__ __device__ constexpr bool is_fhn(int model) { return model == CRD_FHN_TORUS || model == CRD_FHN_FLAT; }
+
+// ---- per-point arithmetic ---------------------------------------------------------------------------
+// EXACT: the reference's expression tree with separately rounded operations.
+template <int MODEL>
+__device__ __forceinline__ double stencil_exact(const RhsConst &k, double a1, double a3, double uC, double uW,
+                                                double uE, double uS, double uN) {
+  if (is_torus(MODEL)) {
+    // :535-537   Diff*(a1*(uE-uW))/(2dx) + Diff*((1/r^2)*(uE-2uC+uW))/(dx*dx) + Diff*(a3*(uN-2uC+uS))/(dy*dy)
+    const double two_uC = __dmul_rn(2.0, uC);
+    const double T1 = __ddiv_rn(__dmul_rn(k.Diff, __dmul_rn(a1, __dsub_rn(uE, uW))), k.twodx);
+    const double T2 = __ddiv_rn(__dmul_rn(k.Diff, __dmul_rn(k.inv_rr, __dadd_rn(__dsub_rn(uE, two_uC), uW))), k.dxdx);
+    const double T3 = __ddiv_rn(__dmul_rn(k.Diff, __dmul_rn(a3, __dadd_rn(__dsub_rn(uN, two_uC), uS))), k.dydy);
+    return __dadd_rn(__dadd_rn(T1, T2), T3);
+  } else {
+    // FHNmodel_flat.cpp:496-498   cu1*(uW+uE) + cu2*(uS+uN) + cu3*uC
+    return __dadd_rn(__dadd_rn(__dmul_rn(k.cu1, __dadd_rn(uW, uE)), __dmul_rn(k.cu2, __dadd_rn(uS, uN))),
+                     __dmul_rn(k.cu3, uC));
+  }
+}
+
+template <int MODEL>
+__device__ __forceinline__ double stencil_fast(const RhsConst &k, double c1, double c3, double uC, double uW,
+                                               double uE, double uS, double uN) {
+  if (is_torus(MODEL)) {
+    const double m2 = -2.0 * uC;
+    return c1 * (uE - uW) + k.c2 * ((uE + m2) + uW) + c3 * ((uN + m2) + uS);
+  } else {
+    return k.cu1 * (uW + uE) + k.cu2 * (uS + uN) + k.cu3 * uC;
+  }
+}
+
+// x^4 rounded once (libm's pow(x, 4.0) is correctly rounded for nearly every argument, (x*x)*(x*x) is not)
+__device__ __forceinline__ double pow4_rn(double x, double x2) {
+  const double e2 = __fma_rn(x, x, -x2);          // x*x = x2 + e2 exactly
+  const double p = __dmul_rn(x2, x2);
+  const double pe = __fma_rn(x2, x2, -p);         // x2*x2 = p + pe exactly
+  return __dadd_rn(p, __fma_rn(__dmul_rn(2.0, x2), e2, pe));
+}
+
+template <int MODEL, bool EXACT>
+__device__ __forceinline__ void react(const RhsConst &k, double b, double u, double v, double &du, double &dv) {
+  if (is_fhn(MODEL)) {
+    if (EXACT) {
+      // :657  ydot_u += 3u - u*u*u - v      :660  ydot_v += EPSILON*(u + b)
+      du = __dadd_rn(du, __dsub_rn(__dsub_rn(__dmul_rn(3.0, u), __dmul_rn(__dmul_rn(u, u), u)), v));
+      dv = __dadd_rn(0.0, __dmul_rn(kEps, __dadd_rn(u, b)));
+    } else {
+      du += (3.0 * u - u * u * u) - v;
+      dv = kEps * (u + b);
+    }
+  } else {
+    // GoldbeterModel_torus.cpp:694-695,715-716; b carries v0 + v1*beta(phi)
+    const double Z = u, Y = v;
+    if (EXACT) {
+      const double z2 = __dmul_rn(Z, Z), y2 = __dmul_rn(Y, Y);
+      const double z4 = pow4_rn(Z, z2);
+      const double v2 = __ddiv_rn(__dmul_rn(G_VM2, z2), __dadd_rn(k.k2n, z2));
+      const double v3 = __ddiv_rn(__dmul_rn(__dmul_rn(G_VM3, y2), z4),
+                                  __dmul_rn(__dadd_rn(k.krm, y2), __dadd_rn(k.kap, z4)));
+      du = __dadd_rn(du, __dsub_rn(__dadd_rn(__dadd_rn(__dsub_rn(b, v2), v3), __dmul_rn(G_kf, Y)), __dmul_rn(G_k, Z)));
+      dv = __dadd_rn(0.0, __dsub_rn(__dsub_rn(v2, v3), __dmul_rn(G_kf, Y)));
+    } else {
+      const double z2 = Z * Z, y2 = Y * Y, z4 = z2 * z2;
+      const double v2 = (G_VM2 * z2) / (k.k2n + z2);
+      const double v3 = (G_VM3 * y2 * z4) / ((k.krm + y2) * (k.kap + z4));
+      const double w = v2 - v3;
+      du += ((b - w) + Y) - G_k * Z;
+      dv = w - Y;
+    }
+  }
+}
+
+// ---- the fused kernel ---------------------------------------------------------------------------------
+// work item = (row group jg, column i); rows j0 = jg*RY .. j0+RY-1 of the slab described by `a`.
+template <int MODEL, bool EXACT, int RY>
+__global__ void __launch_bounds__(256) rhs_kernel(const RhsArgs a) {
+  const long long nx = a.nx, nyl = a.nyl;
+  const long long w = blockIdx.x * 256LL + threadIdx.x;
+  const long long ngroups = (nyl + RY - 1) / RY;
+  if (w >= nx * ngroups) return;
+  const long long jg = w / nx;
+  const long long i = w - jg * nx;
+  const long long j0 = jg * RY;
+  const long long iw = (i == 0) ? nx - 1 : i - 1;
+  const long long ie = (i == nx - 1) ? 0 : i + 1;
+  const int nrows = (nyl - j0 < RY) ? (int)(nyl - j0) : RY;
+
+  const double2 *__restrict__ y2 = reinterpret_cast<const double2 *>(a.y);
+  const double *__restrict__ y = a.y;
+
+  double2 c[RY];
+  double uw[RY], ue[RY];
+  double uu[RY + 2];  // u of rows j0-1 .. j0+RY
+#pragma unroll
+  for (int r = 0; r < RY; ++r) {
+    if (r < nrows) {
+      const long long row = (j0 + r) * nx;
+      c[r] = y2[row + i];
+      uw[r] = y[2 * (row + iw)];
+      ue[r] = y[2 * (row + ie)];
+    } else {
+      c[r] = make_double2(0.0, 0.0); uw[r] = 0.0; ue[r] = 0.0;
+    }
+  }
+  uu[0] = (j0 == 0) ? a.south[i * a.south_stride] : y[2 * ((j0 - 1) * nx + i)];
+  {
+    const long long jn = j0 + nrows;  // row above the last one this thread computes
+    uu[RY + 1] = (jn == nyl) ? a.north[i * a.north_stride] : y[2 * (jn * nx + i)];
+  }
+#pragma unroll
+  for (int r = 0; r < RY; ++r) uu[r + 1] = c[r].x;
+
+  double t1 = 0.0, t3 = 0.0;
+  if (is_torus(MODEL)) {
+    const double2 tc = reinterpret_cast<const double2 *>(a.cth)[i];
+    t1 = tc.x; t3 = tc.y;
+  }
+  double2 *__restrict__ out = reinterpret_cast<double2 *>(a.ydot);
+#pragma unroll
+  for (int r = 0; r < RY; ++r) {
+    if (r < nrows) {
+      const long long jl = j0 + r;
+      const double uN = (r + 1 == nrows) ? uu[RY + 1] : uu[r + 2];
+      const double uS = uu[r];
+      double du = EXACT ? stencil_exact<MODEL>(a.k, t1, t3, c[r].x, uw[r], ue[r], uS, uN)
+                        : stencil_fast<MODEL>(a.k, t1, t3, c[r].x, uw[r], ue[r], uS, uN);
+      double dv = 0.0;
+      if (a.react) {
+        const bool frozen = (a.freeze_north && jl == nyl - 1) || (a.freeze_south && jl == 0);
+        if (frozen) { du = 0.0; dv = 0.0; }
+        else react<MODEL, EXACT>(a.k, a.brow[jl], c[r].x, c[r].y, du, dv);
+      }
+      out[jl * nx + i] = make_double2(du, dv);
+    }
+  }
+}
+
+template <int MODEL, bool EXACT>
+int launch_model(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+  const int variant = g->variant;
+  const int RY = (variant == 1) ? 2 : (variant == 2) ? 8 : (variant == 3) ? 1 : 4;
+  const long long ngroups = (a.nyl + RY - 1) / RY;
+  const long long work = a.nx * ngroups;
+  const long long blocks = (work + 255) / 256;
+  if (blocks <= 0) return 0;
+  if (blocks > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
+  switch (RY) {
+    case 1: rhs_kernel<MODEL, EXACT, 1><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+    case 2: rhs_kernel<MODEL, EXACT, 2><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+    case 8: rhs_kernel<MODEL, EXACT, 8><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+    default: rhs_kernel<MODEL, EXACT, 4><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+  }
+  return check_launch(g->ctx, "rhs_kernel");
+}
+
+int launch_rhs(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+  const bool exact = g->p.arith == CRD_ARITH_EXACT;
+  switch (g->p.model) {
+    case CRD_FHN_TORUS: return exact ? launch_model<CRD_FHN_TORUS, true>(g, a, st) : launch_model<CRD_FHN_TORUS, false>(g, a, st);
+    case CRD_GOLDBETER_TORUS: return exact ? launch_model<CRD_GOLDBETER_TORUS, true>(g, a, st) : launch_model<CRD_GOLDBETER_TORUS, false>(g, a, st);
+    case CRD_FHN_FLAT: return exact ? launch_model<CRD_FHN_FLAT, true>(g, a, st) : launch_model<CRD_FHN_FLAT, false>(g, a, st);
+    case CRD_GOLDBETER_FLAT: return exact ? launch_model<CRD_GOLDBETER_FLAT, true>(g, a, st) : launch_model<CRD_GOLDBETER_FLAT, false>(g, a, st);
+  }
+  set_error("unknown model %d", g->p.model);
+  return -1;
+}
+
+// Arguments for rows [r0, r1) of the slab; south/north describe the rows just outside that range.
+RhsArgs make_args(const crd_grid *g, double t, const double *y, double *ydot, long long r0, long long r1,
+                  const double *south, long long sstride, const double *north, long long nstride) {
+  RhsArgs a;
+  a.y = y + 2 * r0 * g->nx;
+  a.ydot = ydot + 2 * r0 * g->nx;
+  a.south = south; a.south_stride = sstride;
+  a.north = north; a.north_stride = nstride;
+  a.cth = g->cth;
+  a.brow = g->brow + r0;
+  a.nx = g->nx;
+  a.nyl = r1 - r0;
+  const bool tb = t < g->p.t_boundary;
+  a.freeze_south = (tb && g->js == 0 && r0 == 0) ? 1 : 0;
+  a.freeze_north = (tb && g->je == g->ny - 1 && r1 == g->nyl) ? 1 : 0;
+  a.react = (is_fhn(g->p.model) || g->p.just_diffusion == 0) ? 1 : 0;
+  a.k = g->k;
+  return a;
+}
+
+// ---- halo ring: push first/last row into the neighbours' ghost blocks, flag the epoch ------------------
+__global__ void __launch_bounds__(256) halo_push_kernel(const double *__restrict__ y, long long nx, long long nyl,
+                                                        double *prev_north, double *next_south,
+                                                        unsigned long long *prev_flag, unsigned long long *next_flag,
+                                                        unsigned long long *ticket, unsigned long long epoch) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const double *first = y, *last = y + 2 * (nyl - 1) * nx;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nx; i += stride) {
+    prev_north[i] = first[2 * i];   // my row js   is the row above prev's je
+    next_south[i] = last[2 * i];    // my row je   is the row below next's js
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long done = atomicAdd(ticket, 1ULL) + 1ULL;
+    if (done == gridDim.x * epoch) {  // last block of this epoch (ticket is never reset)
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(prev_flag), "l"(epoch) : "memory");
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(next_flag), "l"(epoch) : "memory");
+    }
+  }
+}
+
+__global__ void halo_wait_kernel(const unsigned long long *flag_south, const unsigned long long *flag_north,
+                                 unsigned long long epoch, int *err) {
+  const unsigned long long *f = threadIdx.x == 0 ? flag_south : flag_north;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    if (v >= epoch) break;
+    if (clock64() - t0 > 6000000000LL) {  // ~3 s: a neighbour never posted; report instead of hanging
+      *err = 100 + (int)threadIdx.x;
+      __threadfence_system();
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+
+constexpr int kPushBlocks = 16;
+
+// ---- initial conditions -----------------------------------------------------------------------------------
+struct IcArgs {
+  int model, vary_beta, wave_inside, ic_type;
+  long long nx, nyl, js;
+  double dx, dy, xmin, ymin;
+  double wave_length, wave_width, wave_xmin, wave_xmax;
+  double s0, s1, p0, p1;  // steady state, perturbed state
+};
+
+__global__ void __launch_bounds__(256) ic_kernel(const IcArgs a, double2 *__restrict__ y) {
+  const long long w = blockIdx.x * 256LL + threadIdx.x;
+  if (w >= a.nx * a.nyl) return;
+  const long long j = w / a.nx, i = w - j * a.nx;
+  const double yy = __dadd_rn(a.ymin, __dmul_rn((double)(a.js + j), a.dy));
+  const double xx = __dadd_rn(a.xmin, __dmul_rn((double)i, a.dx));
+  double2 v;
+  const bool fhn = is_fhn(a.model), torus = is_torus(a.model);
+  if (a.vary_beta == 0) {
+    bool in;
+    if (torus) {
+      const bool ybox = yy >= a.wave_length && yy <= __dmul_rn(2.0, a.wave_length);
+      if (a.wave_inside == 1) in = xx >= a.wave_xmin && xx <= a.wave_xmax && ybox;
+      else in = (xx >= a.wave_xmin || xx <= a.wave_xmax) && ybox;
+    } else if (fhn) {
+      in = xx >= a.wave_xmin && xx <= a.wave_xmax && yy >= a.wave_length && yy <= __dmul_rn(2.0, a.wave_length);
+    } else {
+      in = xx >= a.wave_xmin && xx <= a.wave_xmax && yy >= __dmul_rn(2.0, a.wave_length) && yy <= __dmul_rn(3.0, a.wave_length);
+    }
+    v = in ? make_double2(a.p0, a.p1) : make_double2(a.s0, a.s1);
+  } else if (fhn) {
+    v = make_double2(1.0, 1.0);
+  } else {
+    v = make_double2(0.4, 1.6);
+    if (a.ic_type == 1) {
+      const bool in = xx >= a.wave_xmin && xx <= a.wave_xmax && yy >= __dmul_rn(2.0, a.wave_length) && yy <= __dmul_rn(3.0, a.wave_length);
+      if (in) v = make_double2(1.4, 2.6);
+    }
+  }
+  y[w] = v;
+}
+
+}  // namespace
+
+// ============================================================================================================
+extern "C" {
+
+int crd_decomp_phi(int64_t ny, int nranks, int rank, int64_t *js, int64_t *je) {
+  if (nranks < 1 || rank < 0 || rank >= nranks || ny < nranks) { set_error("crd_decomp_phi: bad arguments"); return -1; }
+  *js = ny * rank / nranks;
+  *je = ny * (rank + 1) / nranks - 1;
+  return 0;
+}
+
+crd_grid *crd_grid_create(crd_ctx *ctx, const crd_params *p) {
+  if (!ctx || !p) { set_error("crd_grid_create: null argument"); return nullptr; }
+  if (p->model < 0 || p->model > 3) { set_error("crd_grid_create: unknown model %d", p->model); return nullptr; }
+  if (p->nx < 2 || p->ny < 2 || p->js < 0 || p->je < p->js || p->je >= p->ny) {
+    set_error("crd_grid_create: bad extents nx=%lld ny=%lld js=%lld je=%lld", (long long)p->nx, (long long)p->ny,
+              (long long)p->js, (long long)p->je);
+    return nullptr;
+  }
+  if (use(ctx)) return nullptr;
+  crd_grid *g = new crd_grid;
+  g->ctx = ctx; g->p = *p;
+  g->nx = p->nx; g->ny = p->ny; g->js = p->js; g->je = p->je; g->nyl = p->je - p->js + 1;
+  const bool torus = is_torus(p->model);
+  // geometry exactly as main() computes it (FHNmodel_torus.cpp:188-189,233-234; FHNmodel_flat.cpp:173-176,229-230)
+  if (torus) {
+    g->xmin = 0.0; g->xmax = 2.0 * kPI; g->ymin = 0.0; g->ymax = 2.0 * kPI;
+    g->r = p->surface_width / (2.0 * kPI);
+    g->R = p->surface_length / (2.0 * kPI);
+  } else {
+    g->xmin = 0.0; g->xmax = p->surface_width - g->xmin; g->ymin = 0.0; g->ymax = p->surface_length - g->ymin;
+  }
+  g->dx = (g->xmax - g->xmin) / (1.0 * g->nx - 1.0);
+  g->dy = (g->ymax - g->ymin) / (1.0 * g->ny - 1.0);
+  const double Diff = p->diff, dx = g->dx, dy = g->dy, R = g->R, r = g->r;
+  RhsConst &k = g->k;
+  k.Diff = Diff;
+  k.inv_rr = torus ? (1 / (r * r)) : 0.0;
+  k.twodx = 2 * dx; k.dxdx = dx * dx; k.dydy = dy * dy;
+  k.c2 = torus ? Diff * k.inv_rr / k.dxdx : 0.0;
+  k.cu1 = Diff / dx / dx; k.cu2 = Diff / dy / dy; k.cu3 = -2.0 * (k.cu1 + k.cu2);
+  k.k2n = std::pow(G_K2, G_n); k.krm = std::pow(G_KR, G_m); k.kap = std::pow(G_KA, G_p);
+
+  // per-theta metric table (host libm, the reference's expressions :531-537)
+  std::vector<double> cth((size_t)2 * g->nx, 0.0);
+  if (torus) {
+    for (long long i = 0; i < g->nx; ++i) {
+      const double xx = g->xmin + (i) * (dx);
+      const double a1 = (-sin(xx) / (r * (R + r * cos(xx))));
+      const double a3 = (1 / (((R + r * cos(xx))) * ((R + r * cos(xx)))));
+      if (p->arith == CRD_ARITH_EXACT) { cth[2 * i] = a1; cth[2 * i + 1] = a3; }
+      else { cth[2 * i] = Diff * a1 / k.twodx; cth[2 * i + 1] = Diff * a3 / k.dydy; }
+    }
+  }
+  // per-phi beta (:623-632); Goldbeter rows carry v0 + v1*b (:715)
+  std::vector<double> brow((size_t)g->nyl);
+  const bool fhn = is_fhn(p->model);
+  for (long long j = 0; j < g->nyl; ++j) {
+    const double yy = g->ymin + (g->js + j) * (dy);
+    double b = p->beta;
+    const bool vary = fhn ? (p->vary_beta != 0) : (p->vary_beta == 1);
+    if (vary) b = p->beta_min + yy * (p->beta_max - p->beta_min) / (g->ymax - g->ymin);
+    brow[j] = fhn ? b : (G_v0 + G_v1 * b);
+  }
+  cudaError_t e;
+  if ((e = cudaMalloc(&g->cth, cth.size() * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&g->brow, brow.size() * sizeof(double))) != cudaSuccess ||
+      (e = cudaMemcpy(g->cth, cth.data(), cth.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(g->brow, brow.data(), brow.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
+    set_error("crd_grid_create: %s", cudaGetErrorString(e));
+    crd_grid_destroy(g);
+    return nullptr;
+  }
+  // ghost block + push ticket
+  HaloLayout L{g->nx};
+  if ((e = cudaMalloc(&g->halo_local, L.bytes())) != cudaSuccess ||
+      (e = cudaMemset(g->halo_local, 0, L.bytes())) != cudaSuccess ||
+      (e = cudaMalloc(&g->push_ticket, sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(g->push_ticket, 0, sizeof(unsigned long long))) != cudaSuccess) {
+    set_error("crd_grid_create: %s", cudaGetErrorString(e));
+    crd_grid_destroy(g);
+    return nullptr;
+  }
+  return g;
+}
+
+void crd_grid_destroy(crd_grid *g) {
+  if (!g) return;
+  cudaSetDevice(g->ctx->device);
+  cudaStreamSynchronize(g->ctx->stream);
+  if (g->prev_ipc && g->halo_prev) cudaIpcCloseMemHandle(g->halo_prev);
+  if (g->next_ipc && g->halo_next && g->halo_next != g->halo_prev) cudaIpcCloseMemHandle(g->halo_next);
+  cudaFree(g->cth); cudaFree(g->brow); cudaFree(g->halo_local); cudaFree(g->push_ticket);
+  if (g->stage_y) cudaFree(g->stage_y);
+  if (g->stage_ydot) cudaFree(g->stage_ydot);
+  if (g->s_in) cudaStreamDestroy(g->s_in);
+  if (g->s_out) cudaStreamDestroy(g->s_out);
+  for (int i = 0; i < g->n_chunks; ++i) { cudaEventDestroy(g->ev_in[i]); cudaEventDestroy(g->ev_k[i]); }
+  delete[] g->ev_in; delete[] g->ev_k;
+  delete g;
+}
+
+int crd_grid_params(const crd_grid *g, crd_params *out) { if (!g || !out) return -1; *out = g->p; return 0; }
+int64_t crd_grid_local_length(const crd_grid *g) { return g ? 2 * g->nx * g->nyl : 0; }
+int64_t crd_grid_global_length(const crd_grid *g) { return g ? 2 * g->nx * g->ny : 0; }
+double crd_grid_dx(const crd_grid *g) { return g ? g->dx : 0.0; }
+double crd_grid_dy(const crd_grid *g) { return g ? g->dy : 0.0; }
+int64_t crd_grid_rhs_count(const crd_grid *g) { return g ? g->rhs_count : 0; }
+int crd_grid_set_variant(crd_grid *g, int variant) { if (!g) return -1; g->variant = variant; return 0; }
+
+int crd_grid_halo_handle(crd_grid *g, unsigned char handle[CRD_HALO_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == CRD_HALO_HANDLE_BYTES, "handle size");
+  if (!g) return -1;
+  if (use(g->ctx)) return -1;
+  cudaIpcMemHandle_t h;
+  CRD_CUDA(cudaIpcGetMemHandle(&h, g->halo_local));
+  std::memcpy(handle, &h, sizeof h);
+  return 0;
+}
+
+int crd_grid_halo_connect_ipc(crd_grid *g, const unsigned char prev_handle[CRD_HALO_HANDLE_BYTES],
+                              const unsigned char next_handle[CRD_HALO_HANDLE_BYTES]) {
+  if (!g) return -1;
+  if (use(g->ctx)) return -1;
+  cudaIpcMemHandle_t hp, hn;
+  std::memcpy(&hp, prev_handle, sizeof hp);
+  std::memcpy(&hn, next_handle, sizeof hn);
+  void *pp = nullptr, *pn = nullptr;
+  CRD_CUDA(cudaIpcOpenMemHandle(&pp, hp, cudaIpcMemLazyEnablePeerAccess));
+  if (std::memcmp(&hp, &hn, sizeof hp) == 0) pn = pp;  // two ranks: both neighbours are the same block
+  else CRD_CUDA(cudaIpcOpenMemHandle(&pn, hn, cudaIpcMemLazyEnablePeerAccess));
+  g->halo_prev = (char *)pp; g->halo_next = (char *)pn;
+  g->prev_ipc = g->next_ipc = true;
+  g->connected = true;
+  return 0;
+}
+
+int crd_grid_halo_connect_local(crd_grid *g, crd_grid *prev, crd_grid *next) {
+  if (!g || !prev || !next) return -1;
+  if (prev->nx != g->nx || next->nx != g->nx) { set_error("halo_connect_local: theta mesh differs"); return -1; }
+  if (use(g->ctx)) return -1;
+  for (crd_grid *o : {prev, next}) {
+    if (o->ctx->device != g->ctx->device) {
+      int can = 0;
+      CRD_CUDA(cudaDeviceCanAccessPeer(&can, g->ctx->device, o->ctx->device));
+      if (!can) { set_error("device %d cannot access device %d", g->ctx->device, o->ctx->device); return -1; }
+      cudaError_t e = cudaDeviceEnablePeerAccess(o->ctx->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); return -1; }
+      cudaGetLastError();
+    }
+  }
+  g->halo_prev = prev->halo_local; g->halo_next = next->halo_local;
+  g->prev_ipc = g->next_ipc = false;
+  g->connected = true;
+  return 0;
+}
+
+int crd_rhs_post_halo(crd_grid *g, const double *y) {
+  if (!g || !y) { set_error("crd_rhs_post_halo: null argument"); return -1; }
+  if (!g->connected) return 0;  // single rank: the slab wraps onto itself
+  if (use(g->ctx)) return -1;
+  if (g->epoch != g->computed) { set_error("crd_rhs_post_halo: previous epoch was posted but never computed"); return -1; }
+  g->epoch++;
+  HaloLayout L{g->nx};
+  const int par = (int)(g->epoch & 1ULL);
+  halo_push_kernel<<<kPushBlocks, 256, 0, g->ctx->stream>>>(
+      y, g->nx, g->nyl, (double *)(g->halo_prev + L.ghost_off(par, 1)), (double *)(g->halo_next + L.ghost_off(par, 0)),
+      (unsigned long long *)(g->halo_prev + L.flag_off(1)), (unsigned long long *)(g->halo_next + L.flag_off(0)),
+      g->push_ticket, g->epoch);
+  return check_launch(g->ctx, "halo_push_kernel");
+}
+
+int crd_rhs_compute(crd_grid *g, double t, const double *y, double *ydot) {
+  if (!g || !y || !ydot) { set_error("crd_rhs_compute: null argument"); return -1; }
+  if (use(g->ctx)) return -1;
+  cudaStream_t st = g->ctx->stream;
+  RhsArgs a;
+  if (!g->connected) {
+    a = make_args(g, t, y, ydot, 0, g->nyl, y + 2 * (g->nyl - 1) * g->nx, 2, y, 2);
+  } else {
+    if (g->epoch == g->computed) { set_error("crd_rhs_compute: no halo posted for this evaluation"); return -1; }
+    HaloLayout L{g->nx};
+    const int par = (int)(g->epoch & 1ULL);
+    halo_wait_kernel<<<1, 2, 0, st>>>((const unsigned long long *)(g->halo_local + L.flag_off(0)),
+                                      (const unsigned long long *)(g->halo_local + L.flag_off(1)), g->epoch, g->ctx->err_dev);
+    if (check_launch(g->ctx, "halo_wait_kernel")) return -1;
+    a = make_args(g, t, y, ydot, 0, g->nyl, (const double *)(g->halo_local + L.ghost_off(par, 0)), 1,
+                  (const double *)(g->halo_local + L.ghost_off(par, 1)), 1);
+    g->computed = g->epoch;
+  }
+  if (launch_rhs(g, a, st)) return -1;
+  g->rhs_count++;
+  return 0;
+}
+
+int crd_rhs(crd_grid *g, double t, const double *y, double *ydot) {
+  if (crd_rhs_post_halo(g, y)) return -1;
+  return crd_rhs_compute(g, t, y, ydot);
+}
+
+int crd_f(realtype t, N_Vector y, N_Vector ydot, void *user_data) {
+  crd_grid *g = (crd_grid *)user_data;
+  if (!g || !y || !ydot) return -1;
+  const double *yd = N_VGetDeviceArrayPointer_Crd(y);
+  double *fd = N_VGetDeviceArrayPointer_Crd(ydot);
+  if (!yd || !fd) return -1;
+  if (N_VGetLocalLength_Crd(y) != crd_grid_local_length(g)) { set_error("crd_f: vector length does not match the grid"); return -1; }
+  return crd_rhs(g, t, yd, fd) == 0 ? 0 : -1;
+}
+
+// Host-buffer entry: stream the slab in row chunks, H2D / kernel / D2H on three streams.
+int crd_rhs_host(crd_grid *g, double t, const double *y_host, double *ydot_host) {
+  if (!g || !y_host || !ydot_host) { set_error("crd_rhs_host: null argument"); return -1; }
+  if (g->connected) { set_error("crd_rhs_host: single-rank grids only"); return -1; }
+  if (use(g->ctx)) return -1;
+  const long long nx = g->nx, nyl = g->nyl;
+  const size_t row_bytes = (size_t)2 * nx * sizeof(double);
+  if (!g->stage_y) {
+    CRD_CUDA(cudaMalloc(&g->stage_y, row_bytes * nyl));
+    CRD_CUDA(cudaMalloc(&g->stage_ydot, row_bytes * nyl));
+    CRD_CUDA(cudaStreamCreateWithFlags(&g->s_in, cudaStreamNonBlocking));
+    CRD_CUDA(cudaStreamCreateWithFlags(&g->s_out, cudaStreamNonBlocking));
+    // chunks of ~64 MiB, at least 1 row, at most 64 chunks
+    long long rows_per = (long long)((64ull << 20) / row_bytes);
+    if (rows_per < 1) rows_per = 1;
+    long long n = (nyl + rows_per - 1) / rows_per;
+    if (n > 64) n = 64;
+    if (n < 1) n = 1;
+    g->n_chunks = (int)n;
+    g->ev_in = new cudaEvent_t[n]; g->ev_k = new cudaEvent_t[n];
+    for (int i = 0; i < n; ++i) {
+      CRD_CUDA(cudaEventCreateWithFlags(&g->ev_in[i], cudaEventDisableTiming));
+      CRD_CUDA(cudaEventCreateWithFlags(&g->ev_k[i], cudaEventDisableTiming));
+    }
+  }
+  const int C = g->n_chunks;
+  cudaStream_t sk = g->ctx->stream;
+  auto r_begin = [&](int c) { return nyl * c / C; };
+  // the periodic wrap makes chunk 0 need the last row: send it first
+  CRD_CUDA(cudaMemcpyAsync(g->stage_y + 2 * (nyl - 1) * nx, y_host + 2 * (nyl - 1) * nx, row_bytes, cudaMemcpyHostToDevice, g->s_in));
+  for (int c = 0; c < C; ++c) {
+    const long long r0 = r_begin(c), r1 = r_begin(c + 1);
+    CRD_CUDA(cudaMemcpyAsync(g->stage_y + 2 * r0 * nx, y_host + 2 * r0 * nx, row_bytes * (r1 - r0), cudaMemcpyHostToDevice, g->s_in));
+    CRD_CUDA(cudaEventRecord(g->ev_in[c], g->s_in));
+  }
+  for (int c = 0; c < C; ++c) {
+    const long long r0 = r_begin(c), r1 = r_begin(c + 1);
+    if (r1 == r0) continue;
+    CRD_CUDA(cudaStreamWaitEvent(sk, g->ev_in[c + 1 < C ? c + 1 : c], 0));
+    const double *south = g->stage_y + 2 * ((r0 == 0 ? nyl : r0) - 1) * nx;
+    const double *north = g->stage_y + 2 * (r1 == nyl ? 0 : r1) * nx;
+    RhsArgs a = make_args(g, t, g->stage_y, g->stage_ydot, r0, r1, south, 2, north, 2);
+    if (launch_rhs(g, a, sk)) return -1;
+    CRD_CUDA(cudaEventRecord(g->ev_k[c], sk));
+    CRD_CUDA(cudaStreamWaitEvent(g->s_out, g->ev_k[c], 0));
+    CRD_CUDA(cudaMemcpyAsync(ydot_host + 2 * r0 * nx, g->stage_ydot + 2 * r0 * nx, row_bytes * (r1 - r0), cudaMemcpyDeviceToHost, g->s_out));
+  }
+  CRD_CUDA(cudaStreamSynchronize(g->s_out));
+  CRD_CUDA(cudaStreamSynchronize(sk));
+  g->rhs_count++;
+  return 0;
+}
+
+int crd_fill_initial_conditions(crd_grid *g, const crd_ic_params *ic, double *y_dev) {
+  if (!g || !ic || !y_dev) { set_error("crd_fill_initial_conditions: null argument"); return -1; }
+  if (use(g->ctx)) return -1;
+  IcArgs a;
+  a.model = g->p.model; a.vary_beta = g->p.vary_beta; a.wave_inside = ic->wave_inside; a.ic_type = ic->ic_type;
+  a.nx = g->nx; a.nyl = g->nyl; a.js = g->js;
+  a.dx = g->dx; a.dy = g->dy; a.xmin = g->xmin; a.ymin = g->ymin;
+  // FHNmodel_torus.cpp:199-200,285-296 ; FHNmodel_flat.cpp:274-276
+  a.wave_length = (g->ymax - g->ymin) * ic->wave_length;
+  a.wave_width = (g->xmax - g->xmin) * ic->wave_width;
+  const bool torus = is_torus(g->p.model), fhn = is_fhn(g->p.model);
+  double mid;
+  if (torus) {
+    if (ic->wave_inside == 1) { mid = kPI; a.wave_xmin = mid - a.wave_width / 2.0; a.wave_xmax = mid + a.wave_width / 2.0; }
+    else { mid = 0.0; a.wave_xmin = mid - a.wave_width / 2.0 + (g->xmax - g->xmin); a.wave_xmax = mid + a.wave_width / 2.0; }
+  } else {
+    mid = g->p.surface_width / 2.0; a.wave_xmin = mid - a.wave_width / 2.0; a.wave_xmax = mid + a.wave_width / 2.0;
+  }
+  a.s0 = ic->s0; a.s1 = ic->s1;
+  a.p0 = fhn ? ic->s0 + 2 : ic->s0 + 1;      // Us + 2 | Zs + 1
+  a.p1 = fhn ? ic->s1 + 1.5 : ic->s1 + 1;    // Vs + 1.5 | Ys + 1
+  if (!fhn && g->p.vary_beta == 1 && ic->ic_type == 2) {
+    set_error("icType = 2 (unseeded rand(), GoldbeterModel_flat.cpp:373-374) must be generated on the host");
+    return -1;
+  }
+  const long long work = g->nx * g->nyl;
+  ic_kernel<<<(unsigned)((work + 255) / 256), 256, 0, g->ctx->stream>>>(a, reinterpret_cast<double2 *>(y_dev));
+  return check_launch(g->ctx, "ic_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+"""The C-ABI library builds, loads and exports every symbol include/*.h declares (no GPU needed)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    names = set()
+    for h in ("crd_b200.h", "crd_ark.h", "crd_sundials_compat.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r'extern\s+"C"\s*\{', "", src)
+        # drop every remaining brace block (struct / enum bodies hold function-pointer members)
+        out, depth = [], 0
+        for ch in src:
+            if ch == "{":
+                depth += 1
+            elif ch == "}":
+                depth = max(0, depth - 1)
+            elif depth == 0:
+                out.append(ch)
+        src = "".join(out)
+        src = re.sub(r"typedef[^;]*\(\s*\*\s*\w+\s*\)[^;]*;", "", src)       # function-pointer typedefs
+        src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+        for m in re.finditer(r"\b([A-Za-z_]\w*)\s*\(([^;{}]*)\)\s*;", src):
+            names.add(m.group(1))
+    return sorted(names)
+
+
+def test_header_symbols_exported(crd):
+    handle = C.CDLL(crd.LIB_PATH)
+    names = declared_functions()
+    assert len(names) > 100
+    missing = [n for n in names if not hasattr(handle, n)]
+    assert not missing, missing
+
+
+def test_binding_covers_header(crd):
+    from crdmodel_b200 import _lib
+    assert set(declared_functions()) <= set(_lib.SIGNATURES), set(declared_functions()) - set(_lib.SIGNATURES)
+
+
+def test_no_cpu_fallback(crd):
+    """Without a GPU the product must fail loudly, not compute on the CPU."""
+    if crd.lib().crd_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(crd.CrdError):
+        crd.Context(0)
+
+
+def test_product_does_not_import_oracle():
+    """Only tests/, bench.py and __graft_entry__.py may touch oracle/."""
+    pkg = os.path.join(ROOT, "crdmodel_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".c", ".h", ".hpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "crd_oracle" not in txt \
+                    and "liboracle" not in txt and "_ref" not in txt.replace("halo_ref", ""), os.path.join(dirpath, f)
+
+
+def test_decomp_phi_matches_reference_formula(crd):
+    for ny in (1600, 400, 16384, 1601, 37):
+        for nr in (1, 2, 3, 4, 8):
+            rows = []
+            for r in range(nr):
+                js, je = crd.decomp_phi(ny, nr, r)
+                assert js == ny * r // nr and je == ny * (r + 1) // nr - 1
+                rows += list(range(js, je + 1))
+            assert rows == list(range(ny))

@@ -1,0 +1,184 @@
+"""Parity of the CUDA right-hand side (through the C ABI) with the CPU checker.
+
+Bar: FHN (torus, flat) and Goldbeter-flat stencil in EXACT arithmetic are BIT-IDENTICAL to the
+reference's f(); Goldbeter EXACT differs only where libm's pow(x,2|4) is not correctly rounded
+(<= a few ulp of the summed terms); FAST arithmetic is within 1e-12 relative to the magnitude of the
+summed terms (the north-star tolerance, SURVEY.md §7 "cancellation in the parity metric")."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rhs_golden.npz")
+MODELS = ["fhn_torus", "gb_torus", "fhn_flat", "gb_flat"]
+
+
+def gpu_rhs(crd, ctx, model, nx, ny, t, y, arith, variant=0, **kw):
+    P = crd.make_params(model, nx, ny, arith=arith, **kw)
+    g = crd.Grid(ctx, P)
+    g.set_variant(variant)
+    yv = crd.NVector.from_numpy(ctx, y)
+    dv = g.new_vector()
+    crd.N_VConst(-777.0, dv)
+    g.f(t, yv, dv)
+    out = dv.to_numpy()
+    g.close()
+    return out
+
+
+def scale_of(oracle, P, y):
+    """Per-point magnitude of the summed terms: |f| evaluated term-wise is bounded by f on |y| with the
+    diffusion weights; a cheap upper bound is max(|ref|, local |y| stencil sum)."""
+    ny, nx = P.ny, P.nx
+    a = np.abs(y.reshape(ny, nx, 2))
+    u = a[..., 0]
+    nb = u + np.roll(u, 1, 0) + np.roll(u, -1, 0) + np.roll(u, 1, 1) + np.roll(u, -1, 1)
+    dx = (2 * np.pi if P.model in (0, 1) else P.surface_width) / (nx - 1)
+    dy = (2 * np.pi if P.model in (0, 1) else P.surface_length) / (ny - 1)
+    r2 = (P.surface_width / (2 * np.pi)) ** 2 if P.model in (0, 1) else 1.0
+    Rm = (P.surface_length - P.surface_width) / (2 * np.pi) if P.model in (0, 1) else 1.0
+    s = P.diff * nb * (4.0 / (r2 * dx * dx) + 4.0 / (Rm * Rm * dy * dy)) + 700.0 * (1 + a[..., 0] + a[..., 1])
+    return np.repeat(s[..., None], 2, axis=2).ravel()
+
+
+def test_golden_vectors(crd, ctx, oracle):
+    g = np.load(GOLDEN)
+    for k, row in enumerate(g["meta"]):
+        m, nx, ny, t, vb, jd, seed = int(row[0]), int(row[1]), int(row[2]), float(row[3]), int(row[4]), int(row[5]), int(row[6])
+        ref = g["ydot_%03d" % k]
+        y = oracle.fill_state(m, 2 * nx * ny, seed=seed)
+        kw = dict(vary_beta=vb, just_diffusion=jd, t_boundary=38.0)
+        got = gpu_rhs(crd, ctx, m, nx, ny, t, y, crd.ARITH_EXACT, **kw)
+        P = oracle.make_params(m, nx, ny, **kw)
+        if m in (0, 2) or jd == 1:
+            assert got.tobytes() == ref.tobytes(), ("exact", k, m, nx, ny, t, vb, jd)
+        else:
+            assert np.all(np.abs(got - ref) <= 4e-16 * scale_of(oracle, P, y)), ("gb exact", k)
+        fast = gpu_rhs(crd, ctx, m, nx, ny, t, y, crd.ARITH_FAST, **kw)
+        assert np.all(np.abs(fast - ref) <= 1e-12 * scale_of(oracle, P, y)), ("fast", k, np.abs(fast - ref).max())
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_parity_vs_oracle(crd, ctx, oracle, model, variant):
+    for (nx, ny) in ((400, 1600) if variant == 0 else (100, 400), (3, 2), (2, 3), (257, 31), (31, 257)):
+        for t in (10.0, 50.0):
+            P = oracle.make_params(model, nx, ny, t_boundary=38.0)
+            y = oracle.fill_state(model, 2 * nx * ny, seed=11 + nx)
+            ref = oracle.rhs(P, t, y)
+            got = gpu_rhs(crd, ctx, model, nx, ny, t, y, crd.ARITH_EXACT, variant, t_boundary=38.0)
+            if model.startswith("fhn"):
+                assert got.tobytes() == ref.tobytes(), (model, variant, nx, ny, t)
+            else:
+                sc = scale_of(oracle, P, y)
+                assert np.all(np.abs(got - ref) <= 4e-16 * sc)
+                assert (got != ref).mean() < 0.05      # pow() is correctly rounded almost everywhere
+            fast = gpu_rhs(crd, ctx, model, nx, ny, t, y, crd.ARITH_FAST, variant, t_boundary=38.0)
+            assert np.all(np.abs(fast - ref) <= 1e-12 * scale_of(oracle, P, y))
+
+
+def test_fhn_steady_state_and_constant_field(crd, ctx):
+    beta = 1.25
+    nx, ny = 400, 1600
+    y = np.empty((ny, nx, 2))
+    y[..., 0] = -beta
+    y[..., 1] = beta ** 3 - 3 * beta
+    for model in ("fhn_torus", "fhn_flat"):
+        for arith in (crd.ARITH_EXACT, crd.ARITH_FAST):
+            d = gpu_rhs(crd, ctx, model, nx, ny, 1.0, y, arith, beta=beta, vary_beta=0, t_boundary=0.0)
+            assert np.abs(d).max() < 1e-13
+
+
+def test_phi_split_is_bitwise_invariant(crd, ctx, oracle):
+    """Emulated ranks on one GPU: all slabs post their halo rows first, then all compute (the push never
+    waits, so this order cannot deadlock).  Gathered ydot must equal the single-slab result bit for bit."""
+    for model in MODELS:
+        nx, ny = 96, 203
+        y = oracle.fill_state(model, 2 * nx * ny, seed=5)
+        for t in (10.0, 50.0):
+            one = gpu_rhs(crd, ctx, model, nx, ny, t, y, crd.ARITH_EXACT, t_boundary=38.0)
+            for nr in (1, 2, 3, 8):
+                grids, ys, ds = [], [], []
+                for r in range(nr):
+                    js, je = crd.decomp_phi(ny, nr, r)
+                    g = crd.Grid(ctx, crd.make_params(model, nx, ny, js=js, je=je, t_boundary=38.0))
+                    grids.append(g)
+                    ys.append(crd.NVector.from_numpy(ctx, y[2 * nx * js: 2 * nx * (je + 1)], 2 * nx * ny))
+                    ds.append(g.new_vector())
+                for r in range(nr):
+                    grids[r].halo_connect_local(grids[(r - 1) % nr], grids[(r + 1) % nr])
+                for rep in range(3):   # several epochs: exercises the ghost double-buffering
+                    for r in range(nr):
+                        grids[r].post_halo(ys[r])
+                    for r in range(nr):
+                        grids[r].compute(t, ys[r], ds[r])
+                got = np.concatenate([d.to_numpy() for d in ds])
+                assert got.tobytes() == one.tobytes(), (model, t, nr)
+                ctx.sync()
+                for g in grids:
+                    g.close()
+
+
+def test_host_entry_matches_device_entry(crd, ctx, oracle):
+    nx, ny = 1024, 4099
+    for model in ("fhn_torus", "gb_torus"):
+        y = oracle.fill_state(model, 2 * nx * ny, seed=3)
+        dev = gpu_rhs(crd, ctx, model, nx, ny, 10.0, y, crd.ARITH_EXACT, t_boundary=38.0)
+        g = crd.Grid(ctx, crd.make_params(model, nx, ny, t_boundary=38.0))
+        out = np.empty_like(y)
+        g.f_host(10.0, y, out)
+        assert out.tobytes() == dev.tobytes()
+        g.close()
+
+
+def test_synthetic_state_matches_oracle_stream(crd, ctx, oracle):
+    for model in ("fhn_torus", "gb_torus"):
+        n = 100003
+        v = crd.NVector(ctx, n)
+        ctx.fill_synthetic(model, n, v.device_ptr, seed=0x5EED, first_elem=12345)
+        assert v.to_numpy().tobytes() == oracle.fill_state(model, n, seed=0x5EED, first_elem=12345).tobytes()
+
+
+def test_full_size_properties(crd, ctx):
+    """BASELINE size (16384 x 16384, 4.29 GB per vector): properties that need no CPU pass.
+    (1) uniform steady state -> ydot == 0 to rounding; (2) diffusion-only operator is linear;
+    (3) the frozen rows are exactly zero and nothing else changes between t < tB and t > tB."""
+    nx = ny = 16384
+    n = 2 * nx * ny
+    beta = 1.25
+    g = crd.Grid(ctx, crd.make_params("fhn_torus", nx, ny, arith=crd.ARITH_EXACT, beta=beta, vary_beta=0, t_boundary=38.0))
+    y, d = g.new_vector(), g.new_vector()
+    # (1)
+    import ctypes as C
+    half = crd.NVector(ctx, 2)
+    half.set(np.array([-beta, beta ** 3 - 3 * beta]))
+    # build the uniform state with two strided fills: y = const pair repeated -> use lincomb of synthetic? simpler:
+    crd.N_VConst(-beta, y)                      # u = v = -beta, then fix v through f's linearity in v: f_u = ... - v
+    g.f(50.0, y, d)
+    # with v = -beta instead of Vs: du = 3u - u^3 - v = -3b + b^3 + b, dv = eps*(u + b) = 0
+    assert crd.N_VMaxNorm(d) == pytest.approx(abs(-3 * beta + beta ** 3 + beta), rel=1e-12)
+    # (3)
+    g.fill_synthetic(y)
+    d2 = g.new_vector()
+    g.f(50.0, y, d)
+    g.f(10.0, y, d2)
+    crd.N_VLinearSum(1.0, d, -1.0, d2, d2)     # differs only on rows 0 and ny-1
+    diff = d2.to_numpy().reshape(ny, nx * 2)
+    assert not diff[1:-1].any()
+    assert diff[0].any() and diff[-1].any()
+    del diff
+    # (2) linearity of the diffusion-only Goldbeter operator: f(a*y1 + b*y2) = a f(y1) + b f(y2)
+    g2 = crd.Grid(ctx, crd.make_params("gb_torus", nx, ny, arith=crd.ARITH_FAST, just_diffusion=1))
+    y2 = g.new_vector()
+    ctx.fill_synthetic("gb_torus", n, y2.device_ptr, seed=99)
+    g2.f(0.0, y, d)
+    g2.f(0.0, y2, d2)
+    crd.N_VLinearSum(2.0, d, -0.5, d2, d)       # a f(y1) + b f(y2)
+    crd.N_VLinearSum(2.0, y, -0.5, y2, y)       # a y1 + b y2
+    g2.f(0.0, y, d2)
+    scale = crd.N_VMaxNorm(d)
+    crd.N_VLinearSum(1.0, d, -1.0, d2, d)
+    assert crd.N_VMaxNorm(d) <= 1e-11 * scale
+    g.close(); g2.close()
