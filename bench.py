@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — grid-point RHS evaluations per second of the FHN-torus hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            (N = 1)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      the reference's own f() on the host cores
+
+A "step" is ONE evaluation ydot = f(t, y) over this rank's phi slab through the C ABI (crd_rhs):
+for N > 1 that is the halo push into the neighbours' ghost rows + wait + the fused stencil+reaction
+kernel; for N = 1 it is exactly one kernel launch.  Workload: BASELINE.json configs[3], FHN on the
+torus, synthetic LCG state, theta 16384 x phi 16384 PER GPU (4.29 GB per vector, far larger than the
+126 MB L2), phi-split over the N GPUs (global phi mesh 16384*N): weak scaling.  EXACT arithmetic: the
+device result is bit-identical to the reference's f().
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NX = 16384
+ROWS_PER_GPU = 16384
+BYTES_PER_POINT = 32          # read u,v + write u',v' 
+T_EVAL = 50.0                 # t > tBoundary: no frozen rows
+METRIC = "FHN-torus grid-point RHS evals/sec (fp64)"
+UNIT = "point-RHS/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own f() (oracle/_ref, compiled in place from its sources; the
+    plain-C restatement if that library is absent) on all host cores, emulated MPI ranks = threads."""
+    if rank != 0:
+        return
+    import numpy as np
+    import oracle as O
+    cores = os.cpu_count() or 1
+    have_ref = O.ref_available("fhn_torus")
+    kind = "reference" if have_ref else "port"
+    nranks = cores if have_ref else 1
+    # bounded sample: a phi band of the same 16384-wide grid, sized so (K + W) steps take ~2 min at most
+    probe_rows = 64
+    Pp = O.make_params("fhn_torus", NX, max(probe_rows, 2 * nranks))
+    yp = O.fill_state("fhn_torus", 2 * NX * Pp.ny)
+    if have_ref:
+        _, sec = O.ref_rhs(Pp, T_EVAL, yp, nranks=nranks, reps=1, want_out=False)
+    else:
+        t0 = time.time(); O.rhs(Pp, T_EVAL, yp); sec = time.time() - t0
+    rate = NX * Pp.ny / max(sec, 1e-6)
+    budget = 100.0 / max(1, args.steps + args.warmup)
+    rows = int(min(2048, max(2 * nranks, rate * budget / NX)))
+    P = O.make_params("fhn_torus", NX, rows)
+    y = O.fill_state("fhn_torus", 2 * NX * rows)
+    def step(reps):
+        if have_ref:
+            return O.ref_rhs(P, T_EVAL, y, nranks=nranks, reps=reps, want_out=False)[1]
+        t0 = time.time()
+        for _ in range(reps):
+            O.rhs(P, T_EVAL, y)
+        return time.time() - t0
+    step(max(1, args.warmup))
+    sec = step(args.steps)
+    value = NX * rows * args.steps / sec
+    sample = "FHN torus theta %d x phi %d band, %d f() calls, %d emulated MPI ranks (threads) %s" % (
+        NX, rows, args.steps, nranks, "dims from MPI_Dims_create; timing only: the reference's exchange is wrong for >2 ranks per dimension" if nranks > 2 else "")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "FHN torus RHS f(t,y), theta 16384, bounded phi band of %d rows on the host CPU" % rows,
+                       "nx": NX, "rows": rows, "t": T_EVAL},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nranks, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(budget_s=20.0):
+    """Bounded CPU sample beside the GPU number (rank 0, N = 1): the reference's f() on all host cores."""
+    import oracle as O
+    cores = os.cpu_count() or 1
+    have_ref = O.ref_available("fhn_torus")
+    nranks = cores if have_ref else 1
+    rows = max(256, 2 * nranks)
+    P = O.make_params("fhn_torus", NX, rows)
+    y = O.fill_state("fhn_torus", 2 * NX * rows)
+    if have_ref:
+        _, sec1 = O.ref_rhs(P, T_EVAL, y, nranks=nranks, reps=1, want_out=False)
+        reps = int(max(1, min(200, budget_s / max(sec1, 1e-3) / 2)))
+        _, sec = O.ref_rhs(P, T_EVAL, y, nranks=nranks, reps=reps, want_out=False)
+        _, s1 = O.ref_rhs(P, T_EVAL, y, nranks=1, reps=1, want_out=False)
+        single = NX * rows / s1
+    else:
+        t0 = time.time(); O.rhs(P, T_EVAL, y); sec1 = time.time() - t0
+        reps = int(max(1, min(50, budget_s / max(sec1, 1e-3))))
+        t0 = time.time()
+        for _ in range(reps):
+            O.rhs(P, T_EVAL, y)
+        sec = time.time() - t0
+        single = NX * rows * reps / sec
+    return {"value": NX * rows * reps / sec, "unit": UNIT, "cores": nranks, "kind": "reference" if have_ref else "port",
+            "single_core_value": single,
+            "sample": "reference f() (oracle/_ref, -O2) on theta %d x phi %d, %d calls, %d emulated MPI ranks on %d host cores"
+                      % (NX, rows, reps, nranks, cores)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="crd")
+    ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--rows-per-gpu", type=int, default=ROWS_PER_GPU)
+    ap.add_argument("--nx", type=int, default=NX)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-integrator", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import crdmodel_b200 as crd
+    from crdmodel_b200 import dist as cdist
+
+    torch.cuda.set_device(local_rank)
+    use_dist = world > 1
+    gloo = None
+    if use_dist:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        gloo = dist.new_group(backend="gloo")
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not use_dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    nx, nyl = args.nx, args.rows_per_gpu
+    ny = nyl * world
+    js, je = crd.decomp_phi(ny, world, rank)
+    arith = crd.ARITH_EXACT if args.arith == "exact" else crd.ARITH_FAST
+    ctx = crd.Context(local_rank)
+    grid = crd.Grid(ctx, crd.make_params("fhn_torus", nx, ny, js=js, je=je, arith=arith))
+    if use_dist:
+        ctx.set_comm(rank, world, cdist.make_allreduce(gloo))
+        cdist.ring_connect(grid, rank, world, cdist.exchange_handles(grid.halo_handle(), gloo))
+    y, ydot = grid.new_vector(), grid.new_vector()
+    grid.fill_synthetic(y)
+    points = nx * nyl
+
+    # ---- device-resident throughput -----------------------------------------------------------------
+    for _ in range(args.warmup):
+        grid.f(T_EVAL, y, ydot)
+    ctx.sync()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    launches0 = ctx.launches
+    t_wall0 = time.time()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        grid.f(T_EVAL, y, ydot)
+    ms = ctx.timer_stop()
+    barrier()
+    t_wall1 = time.time()
+    launches = ctx.launches - launches0
+    ms = max_over_ranks(ms)
+    # keep the GPU under the same load a little longer if the timed region was too short to sample clocks
+    probe_note = "timed region"
+    if rank == 0 and t_wall1 - t_wall0 < 0.6:
+        probe_note = "timed region + %d further identical launches (region shorter than the 100 ms sampling period x 6)" % 400
+        for _ in range(400):
+            grid.f(T_EVAL, y, ydot)
+        ctx.sync()
+        t_wall1 = time.time()
+    elif use_dist:
+        pass
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    if clocks is not None:
+        clocks["sampled_over"] = probe_note
+    barrier()
+    ms_per_step = ms / args.steps
+    value = world * points * args.steps / (ms * 1e-3)
+
+    # ---- end to end: host buffers through crd_rhs_host, H2D + D2H inside the timed region ----------
+    nbytes = 16 * points
+    lib = crd.lib()
+    hy = lib.crd_malloc_host(nbytes)
+    hd = lib.crd_malloc_host(nbytes)
+    if not hy or not hd:
+        raise crd.CrdError("cannot allocate pinned host buffers")
+    crd._lib.check(lib.crd_memcpy_d2h(ctx._h, hy, y.device_ptr, nbytes), "stage host state")
+    grid.f_host(T_EVAL, hy, hd)      # warm-up (allocates the staging buffers)
+    barrier()
+    t0 = time.time()
+    for _ in range(args.e2e_steps):
+        grid.f_host(T_EVAL, hy, hd)
+    ctx.sync()
+    e2e_s = max_over_ranks(time.time() - t0)
+    e2e_value = world * points * args.e2e_steps / e2e_s
+    # the host result of the last e2e step must be the device result (same kernel, same bits)
+    import ctypes as C
+    probe = np.ctypeslib.as_array(C.cast(hd, C.POINTER(C.c_double)), shape=(2 * nx * min(nyl, 64),))
+    ref = np.empty_like(probe)
+    grid.f(T_EVAL, y, ydot)
+    crd._lib.check(lib.crd_memcpy_d2h(ctx._h, ref.ctypes.data, ydot.device_ptr, ref.nbytes), "read back")
+    e2e_ok = bool(probe.tobytes() == ref.tobytes())
+    lib.crd_free_host(hy); lib.crd_free_host(hd)
+
+    # ---- integrator steps/s (fused N_Vector ops + 6 RHS per step), reported alongside --------------
+    integ = None
+    if not args.no_integrator:
+        try:
+            solver = crd.ARKodeSolver(grid, y, t0=T_EVAL, fused=True)
+            solver.set_init_step(1e-9)
+            flag, _ = solver.ARKode(T_EVAL + 1.0, crd.ARK_ONE_STEP)   # set-up + first step
+            ctx.sync(); barrier()
+            n0 = solver.stats()
+            t0 = time.time()
+            nsteps = 10
+            for _ in range(nsteps):
+                flag, tcur = solver.ARKode(T_EVAL + 1.0, crd.ARK_ONE_STEP)
+                if flag < 0:
+                    break
+            ctx.sync()
+            dt = max_over_ranks(time.time() - t0)
+            n1 = solver.stats()
+            integ = {"steps_per_s": (n1["nst"] - n0["nst"]) / dt, "step_attempts_per_s": (n1["nst_attempts"] - n0["nst_attempts"]) / dt,
+                     "nst": n1["nst"] - n0["nst"], "nfe": n1["nfe"] - n0["nfe"], "netf": n1["netf"] - n0["netf"],
+                     "rhs_per_step": (n1["nfe"] - n0["nfe"]) / max(1, n1["nst_attempts"] - n0["nst_attempts"]),
+                     "flag": flag, "method": "Zonneveld 5-3-4 explicit RK, rtol 1e-5 atol 1e-10, fused stage/finish kernels"}
+            solver.free()
+        except Exception as e:  # the headline metric does not depend on this block
+            integ = {"error": str(e)[:200]}
+
+    if rank == 0:
+        peaks, peaks_src = measured_peaks()
+        achieved = BYTES_PER_POINT * points / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("rhs_kernel_fhn_torus_%s_%dx%d" % (args.arith, nx, nyl))
+            except Exception:
+                traffic = None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "BASELINE configs[3]: FHN torus RHS f(t,y), synthetic LCG state, theta %d x phi %d per GPU "
+                                       "(global phi %d), phi-split ring of %d GPU(s)" % (nx, nyl, ny, world),
+                           "arith": args.arith + (" (bit-identical to the reference f())" if args.arith == "exact" else " (<=1e-12)"),
+                           "nx": nx, "rows_per_gpu": nyl, "ny_global": ny, "t": T_EVAL,
+                           "l2": "inputs larger than L2 (%.2f GB per vector vs 126 MB)" % (nbytes / 1e9),
+                           "parallelism": "phi-split x%d, P2P halo rows over NVLink" % world},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_src,
+                             "kernel": "rhs_kernel<FHN_TORUS,%s,RY=4>" % args.arith, "bytes_per_point": BYTES_PER_POINT,
+                             "points_per_launch": points},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                        "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
+                        "matches_device_result": e2e_ok, "api": "crd_rhs_host (C ABI, pinned host buffers, chunked 3-stream pipeline)"},
+                "gpu_launches": int(launches), "clocks": clocks, "integrator": integ}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline()
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % str(e)[:120]}
+        print(json.dumps(line), flush=True)
+
+    y.destroy(); ydot.destroy(); grid.close(); ctx.close()
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -14,6 +14,7 @@ struct RhsConst {
   double twodx;    // 2*dx
   double dxdx;     // dx*dx
   double dydy;     // dy*dy
+  double r_twodx, r_dxdx, r_dydy;  // RN(1/x) of the three divisors (host IEEE division)
   // torus, fast: folded
   double c2;       // Diff*inv_rr/dxdx
   // flat (FHNmodel_flat.cpp:489-491)
@@ -36,6 +37,8 @@ struct RhsArgs {
   int freeze_south;      // t < tBoundary && js == 0       (:649)
   int freeze_north;      // t < tBoundary && je == ny-1    (:643)
   int react;             // 0 only for Goldbeter with justDiffusion (:668)
+  int div_shift;         // >= 0: work item / nx by multiply-shift (set at launch)
+  unsigned div_magic;
   RhsConst k;
 };
 

