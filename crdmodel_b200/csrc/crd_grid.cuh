@@ -15,6 +15,7 @@ struct RhsConst {
   double dxdx;     // dx*dx
   double dydy;     // dy*dy
   double r_twodx, r_dxdx, r_dydy;  // RN(1/x) of the three divisors (host IEEE division)
+  int div_safe;    // divisors positive and within 2^+-90: the reciprocal-refinement division applies
   // torus, fast: folded
   double c2;       // Diff*inv_rr/dxdx
   // flat (FHNmodel_flat.cpp:489-491)
@@ -28,9 +29,8 @@ struct RhsConst {
 struct RhsArgs {
   const double *y;
   double *ydot;
-  const double *south;   // u of global row js-1:  south[i*south_stride]
-  const double *north;   // u of global row je+1:  north[i*north_stride]
-  long long south_stride, north_stride;
+  const double *south;   // the row below the slab's first row (global row js-1), same [nx][2] layout
+  const double *north;   // the row above the slab's last row  (global row je+1)
   const double *cth;     // [nx][2]: exact (a1, a3) | fast (c1, c3); unused for flat
   const double *brow;    // [nyl]: FHN b(phi) | Goldbeter v0 + v1*b(phi)
   long long nx, nyl;
@@ -43,12 +43,12 @@ struct RhsArgs {
 };
 
 // ghost block, one per grid, cudaMalloc'd so it can be exported with cudaIpcGetMemHandle:
-//   double ghost[2 parity][2 side][nx]     side 0 = south (row js-1), side 1 = north (row je+1)
+//   double ghost[2 parity][2 side][nx][2]  side 0 = south (row js-1), side 1 = north (row je+1); whole (u,v) rows
 //   unsigned long long flag[2 side]        epoch of the last complete push, 128 B apart
 struct HaloLayout {
   long long nx;
-  __host__ __device__ size_t ghost_off(int parity, int side) const { return (size_t)(parity * 2 + side) * (size_t)nx * sizeof(double); }
-  __host__ __device__ size_t flag_off(int side) const { return (size_t)4 * (size_t)nx * sizeof(double) + 128 + (size_t)side * 128; }
+  __host__ __device__ size_t ghost_off(int parity, int side) const { return (size_t)(parity * 2 + side) * (size_t)nx * 2 * sizeof(double); }
+  __host__ __device__ size_t flag_off(int side) const { return (size_t)4 * (size_t)nx * 2 * sizeof(double) + 128 + (size_t)side * 128; }
   __host__ __device__ size_t bytes() const { return flag_off(1) + 128; }
 };
 

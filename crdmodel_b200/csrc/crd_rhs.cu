@@ -38,8 +38,9 @@ __host__ __device__ constexpr bool is_fhn(int model) { return model == CRD_FHN_T
 // division so signed zeros and subnormals also match.
 __device__ __forceinline__ double div_const_rn(double a, double c, double rc) {
   double q = __dmul_rn(a, rc);
-  const double aq = fabs(q);
-  if (aq > 0x1p-900 && aq < 0x1p900) {
+  // biased exponent of q in [123, 1923)  <=>  2^-900 <= |q| < 2^900 (integer test: keeps the FP64 pipe free)
+  const unsigned eq = ((unsigned)__double2hiint(q) >> 20) & 0x7ffu;
+  if (eq - 123u < 1800u) {
     double r = __fma_rn(-q, c, a);
     q = __fma_rn(r, rc, q);
     r = __fma_rn(-q, c, a);
@@ -47,6 +48,25 @@ __device__ __forceinline__ double div_const_rn(double a, double c, double rc) {
   }
   if (a == 0.0) return q;  // (+-0)*rc carries the sign of a/c; uniform regions of the field take this exit
   return __ddiv_rn(a, c);
+}
+
+// Straight-line form used by the stencil (so the three divisions of a point and the points of a thread
+// interleave and hide the FP64 latency).  Needs c > 0.  The residual is formed as r' = q*c - a and
+// subtracted, which makes a zero numerator come out as the correctly signed zero with no special case:
+//   a = -0: q0 = -0, r' = fma(-0, c, +0) = +0, q = fma(-(+0), rc, -0) = -0;   a = +0: likewise +0.
+__device__ __forceinline__ double div_const_line(double a, double c, double rc) {
+  const double q0 = __dmul_rn(a, rc);
+  double r = __fma_rn(q0, c, -a);
+  const double q1 = __fma_rn(-r, rc, q0);
+  r = __fma_rn(q1, c, -a);
+  return __fma_rn(-r, rc, q1);
+}
+// true when the numerator is outside the range where div_const_line is proven (|n| in [2^-800, 2^800),
+// divisor within 2^+-90, checked on the host) and is not an exact zero; integer tests only
+__device__ __forceinline__ bool div_needs_ieee(double n) {
+  const unsigned hi = (unsigned)__double2hiint(n) & 0x7fffffffu;
+  const bool inrange = (hi - 0x0DF00000u) < 0x64000000u;   // biased exponent in [223, 1823)
+  return !inrange && (hi | (unsigned)__double2loint(n)) != 0u;
 }
 
 // 1/x to ~1 ulp without the IEEE slow path (FAST arithmetic only; x is a sum of positive terms here)
@@ -61,6 +81,11 @@ __device__ __forceinline__ double rcp_fast(double x) {
   return fma(r, e, r);
 }
 
+// the same sum with IEEE divisions; kept out of line so the unrolled hot loop does not carry 3 divisions per row
+__device__ __noinline__ double stencil_sum_ieee(double n1, double n2, double n3, double c1, double c2, double c3) {
+  return __dadd_rn(__dadd_rn(__ddiv_rn(n1, c1), __ddiv_rn(n2, c2)), __ddiv_rn(n3, c3));
+}
+
 // EXACT: the reference's expression tree with separately rounded operations.
 template <int MODEL>
 __device__ __forceinline__ double stencil_exact(const RhsConst &k, double a1, double a3, double uC, double uW,
@@ -68,9 +93,14 @@ __device__ __forceinline__ double stencil_exact(const RhsConst &k, double a1, do
   if (is_torus(MODEL)) {
     // :535-537   Diff*(a1*(uE-uW))/(2dx) + Diff*((1/r^2)*(uE-2uC+uW))/(dx*dx) + Diff*(a3*(uN-2uC+uS))/(dy*dy)
     const double two_uC = __dmul_rn(2.0, uC);
-    const double T1 = div_const_rn(__dmul_rn(k.Diff, __dmul_rn(a1, __dsub_rn(uE, uW))), k.twodx, k.r_twodx);
-    const double T2 = div_const_rn(__dmul_rn(k.Diff, __dmul_rn(k.inv_rr, __dadd_rn(__dsub_rn(uE, two_uC), uW))), k.dxdx, k.r_dxdx);
-    const double T3 = div_const_rn(__dmul_rn(k.Diff, __dmul_rn(a3, __dadd_rn(__dsub_rn(uN, two_uC), uS))), k.dydy, k.r_dydy);
+    const double n1 = __dmul_rn(k.Diff, __dmul_rn(a1, __dsub_rn(uE, uW)));
+    const double n2 = __dmul_rn(k.Diff, __dmul_rn(k.inv_rr, __dadd_rn(__dsub_rn(uE, two_uC), uW)));
+    const double n3 = __dmul_rn(k.Diff, __dmul_rn(a3, __dadd_rn(__dsub_rn(uN, two_uC), uS)));
+    double T1 = div_const_line(n1, k.twodx, k.r_twodx);
+    double T2 = div_const_line(n2, k.dxdx, k.r_dxdx);
+    double T3 = div_const_line(n3, k.dydy, k.r_dydy);
+    if (!k.div_safe || div_needs_ieee(n1) || div_needs_ieee(n2) || div_needs_ieee(n3))
+      return stencil_sum_ieee(n1, n2, n3, k.twodx, k.dxdx, k.dydy);  // tiny / huge / non-finite numerator: rare, out of line
     return __dadd_rn(__dadd_rn(T1, T2), T3);
   } else {
     // FHNmodel_flat.cpp:496-498   cu1*(uW+uE) + cu2*(uS+uN) + cu3*uC
@@ -165,10 +195,10 @@ __global__ void __launch_bounds__(256, MINB) rhs_kernel(const RhsArgs a) {
       c[r] = make_double2(0.0, 0.0); uw[r] = 0.0; ue[r] = 0.0;
     }
   }
-  uu[0] = (j0 == 0) ? a.south[i * a.south_stride] : y[2 * ((j0 - 1) * nx + i)];
+  uu[0] = (j0 == 0) ? a.south[2 * i] : y[2 * ((j0 - 1) * nx + i)];
   {
     const long long jn = j0 + nrows;  // row above the last one this thread computes
-    uu[RY + 1] = (jn == nyl) ? a.north[i * a.north_stride] : y[2 * (jn * nx + i)];
+    uu[RY + 1] = (jn == nyl) ? a.north[2 * i] : y[2 * (jn * nx + i)];
   }
 #pragma unroll
   for (int r = 0; r < RY; ++r) uu[r + 1] = c[r].x;
@@ -198,10 +228,144 @@ __global__ void __launch_bounds__(256, MINB) rhs_kernel(const RhsArgs a) {
   }
 }
 
+// ---- the tiled kernel: row segments staged in shared memory by 1-D TMA bulk copies ---------------------
+// One CTA = one tile of TX theta columns x TY phi rows.  An elected thread arms an mbarrier with the tile's
+// byte count and issues one cp.async.bulk (UBLKCP) per tile row: (TX+2) points of rows j0-1 .. j0+TY, the
+// wrap columns and the ghost rows as separate small copies.  No thread computes a global load address for
+// the state; the stencil reads its neighbours from shared memory at compile-time offsets, the column's
+// previous/next row stay in registers while it marches, results leave as coalesced 16-byte stores.
+// Resident CTAs of the same SM overlap each other's load / compute / store phases.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+template <int MODEL, bool EXACT, int TX, int TY, int MINB>
+__global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
+  constexpr int PITCH = TX + 2;            // points per staged row (west halo + TX + east halo)
+  constexpr int RPT = TY * TX / 256;       // rows marched by one thread
+  static_assert(256 % TX == 0 && (TY * TX) % 256 == 0, "tile shape");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double2 *tile = reinterpret_cast<double2 *>(smem_raw);                      // [TY+2][PITCH]
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)(TY + 2) * PITCH * 16);
+
+  const long long nx = a.nx, nyl = a.nyl;
+  const long long tiles_x = (nx + TX - 1) / TX;
+  const long long ty = blockIdx.x / tiles_x;
+  const long long tx = blockIdx.x - ty * tiles_x;
+  const long long i0 = tx * TX, j0 = ty * TY;
+  const int w = (nx - i0 < TX) ? (int)(nx - i0) : TX;            // valid columns of this tile
+  const int h = (nyl - j0 < TY) ? (int)(nyl - j0) : TY;          // valid rows of this tile
+  const unsigned bar = smem_u32(mbar);
+
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const bool west_in = i0 > 0, east_in = i0 + w < nx;           // halo column contiguous with the tile?
+    const unsigned row_bytes = (unsigned)(w + (west_in ? 1 : 0) + (east_in ? 1 : 0)) * 16u;
+    const unsigned total = (unsigned)(h + 2) * (unsigned)(w + 2) * 16u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+    const double2 *y2 = reinterpret_cast<const double2 *>(a.y);
+    for (int r = 0; r < h + 2; ++r) {
+      const long long jr = j0 - 1 + r;
+      const double2 *row = (jr < 0) ? reinterpret_cast<const double2 *>(a.south)
+                         : (jr >= nyl) ? reinterpret_cast<const double2 *>(a.north) : y2 + jr * nx;
+      const unsigned dst = smem_u32(tile + r * PITCH);
+      bulk_g2s(dst + (west_in ? 0u : 16u), row + i0 - (west_in ? 1 : 0), row_bytes, bar);
+      if (!west_in) bulk_g2s(dst, row + (nx - 1), 16u, bar);                    // theta wrap: column nx-1
+      if (!east_in) bulk_g2s(dst + (unsigned)(w + 1) * 16u, row, 16u, bar);     // theta wrap: column 0
+    }
+  }
+  __syncthreads();   // barrier initialised before anyone polls it
+
+  const int c = threadIdx.x % TX;          // column inside the tile
+  const int g0 = (threadIdx.x / TX) * RPT; // first tile row of this thread
+  double t1 = 0.0, t3 = 0.0;
+  const bool active = c < w && g0 < h;
+  if (is_torus(MODEL) && active) {
+    const double2 tc = reinterpret_cast<const double2 *>(a.cth)[i0 + c];
+    t1 = tc.x; t3 = tc.y;
+  }
+  // wait for the tile (phase 0)
+  {
+    unsigned ok = 0;
+    while (!ok) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(bar) : "memory");
+    }
+  }
+  if (!active) return;
+
+  const double2 *col = tile + (g0 + 1) * PITCH + (c + 1);   // centre of this thread's first row
+  double uS = col[-PITCH].x;
+  double2 cc = col[0];
+  double2 *out = reinterpret_cast<double2 *>(a.ydot) + (j0 + g0) * nx + (i0 + c);
+  const int nrows = (h - g0 < RPT) ? (h - g0) : RPT;
+  // frozen rows (t < tBoundary): only slab row 0 / nyl-1 can be one; express them as tile-local row numbers
+  const int fr_s = (a.freeze_south && j0 + g0 == 0) ? 0 : -1;
+  const int fr_n = (a.freeze_north && nyl - 1 - (j0 + g0) < RPT) ? (int)(nyl - 1 - (j0 + g0)) : -1;
+  const double *__restrict__ brow = a.brow + (j0 + g0);
+  const int react_on = a.react;
+  auto row = [&](int r) {
+    const double2 nn = col[(r + 1) * PITCH];
+    const double uW = col[r * PITCH - 1].x, uE = col[r * PITCH + 1].x;
+    double du = EXACT ? stencil_exact<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x)
+                      : stencil_fast<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x);
+    double dv = 0.0;
+    if (react_on) {
+      react<MODEL, EXACT>(a.k, __ldg(brow + r), cc.x, cc.y, du, dv);
+      const bool frozen = (r == fr_s) || (r == fr_n);
+      du = frozen ? 0.0 : du;
+      dv = frozen ? 0.0 : dv;
+    }
+    *out = make_double2(du, dv);
+    out += nx;
+    uS = cc.x;
+    cc = nn;
+  };
+  if (nrows == RPT) {   // full tile: straight-line code, rows interleave
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) row(r);
+  } else {
+    for (int r = 0; r < nrows; ++r) row(r);
+  }
+}
+
+template <int MODEL, bool EXACT, int TX, int TY, int MINB>
+int launch_tile(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+  const long long tiles = ((a.nx + TX - 1) / TX) * ((a.nyl + TY - 1) / TY);
+  if (tiles <= 0) return 0;
+  if (tiles > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
+  const size_t smem = (size_t)(TY + 2) * (TX + 2) * 16 + 16;
+  auto kern = rhs_tile_kernel<MODEL, EXACT, TX, TY, MINB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+    attr_set = true;
+  }
+  kern<<<(unsigned)tiles, 256, smem, st>>>(a);
+  return check_launch(g->ctx, "rhs_tile_kernel");
+}
+
 template <int MODEL, bool EXACT>
 int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
-  // variant -> (rows per thread, min resident CTAs/SM): 0 (4,4) default | 1 (2,4) | 2 (8,2) | 3 (1,4) | 4 (4,3)
-  const int variant = g->variant;
+  // variant 0 = automatic: the TMA-tiled kernel wherever a tile row is reasonably full, the direct kernel on
+  // narrow meshes (the reference's default 100- and 400-wide grids are L2-resident and launch-bound anyway).
+  // explicit: direct kernel (rows per thread, min CTAs/SM) 1 (2,4) | 2 (8,2) | 3 (1,4) | 4 (4,3) | 5 (4,4)
+  //           tiled kernel (TX, TY, min CTAs/SM) 10 (128,16,4) | 11 (128,32,3) | 12 (64,32,4) | 13 (256,16,3) | 14 (128,16,3)
+  int variant = g->variant;
+  if (variant == 0) variant = (a_in.nx >= 192) ? 13 : (a_in.nx >= 96) ? 10 : 5;
+  switch (variant) {
+    case 10: return launch_tile<MODEL, EXACT, 128, 16, 4>(g, a_in, st);
+    case 11: return launch_tile<MODEL, EXACT, 128, 32, 3>(g, a_in, st);
+    case 12: return launch_tile<MODEL, EXACT, 64, 32, 4>(g, a_in, st);
+    case 13: return launch_tile<MODEL, EXACT, 256, 16, 3>(g, a_in, st);
+    case 14: return launch_tile<MODEL, EXACT, 128, 16, 3>(g, a_in, st);
+    default: break;
+  }
   const int RY = (variant == 1) ? 2 : (variant == 2) ? 8 : (variant == 3) ? 1 : 4;
   const long long ngroups = (a_in.nyl + RY - 1) / RY;
   const long long work = a_in.nx * ngroups;
@@ -241,12 +405,12 @@ int launch_rhs(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
 
 // Arguments for rows [r0, r1) of the slab; south/north describe the rows just outside that range.
 RhsArgs make_args(const crd_grid *g, double t, const double *y, double *ydot, long long r0, long long r1,
-                  const double *south, long long sstride, const double *north, long long nstride) {
+                  const double *south, const double *north) {
   RhsArgs a;
   a.y = y + 2 * r0 * g->nx;
   a.ydot = ydot + 2 * r0 * g->nx;
-  a.south = south; a.south_stride = sstride;
-  a.north = north; a.north_stride = nstride;
+  a.south = south;
+  a.north = north;
   a.cth = g->cth;
   a.brow = g->brow + r0;
   a.nx = g->nx;
@@ -265,10 +429,12 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const double *__restrict
                                                         unsigned long long *prev_flag, unsigned long long *next_flag,
                                                         unsigned long long *ticket, unsigned long long epoch) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  const double *first = y, *last = y + 2 * (nyl - 1) * nx;
+  const double2 *first = reinterpret_cast<const double2 *>(y);
+  const double2 *last = reinterpret_cast<const double2 *>(y + 2 * (nyl - 1) * nx);
+  double2 *pn = reinterpret_cast<double2 *>(prev_north), *ns = reinterpret_cast<double2 *>(next_south);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nx; i += stride) {
-    prev_north[i] = first[2 * i];   // my row js   is the row above prev's je
-    next_south[i] = last[2 * i];    // my row je   is the row below next's js
+    pn[i] = first[i];   // my row js is the row above prev's je
+    ns[i] = last[i];    // my row je is the row below next's js
   }
   __threadfence_system();
   __syncthreads();
@@ -383,6 +549,12 @@ crd_grid *crd_grid_create(crd_ctx *ctx, const crd_params *p) {
   k.inv_rr = torus ? (1 / (r * r)) : 0.0;
   k.twodx = 2 * dx; k.dxdx = dx * dx; k.dydy = dy * dy;
   k.r_twodx = 1.0 / k.twodx; k.r_dxdx = 1.0 / k.dxdx; k.r_dydy = 1.0 / k.dydy;
+  {
+    // the reciprocal-refinement division is proven for positive divisors of moderate magnitude only
+    k.div_safe = 1;
+    for (double c : {k.twodx, k.dxdx, k.dydy})
+      if (!(c > 0x1p-90 && c < 0x1p90)) k.div_safe = 0;
+  }
   k.c2 = torus ? Diff * k.inv_rr / k.dxdx : 0.0;
   k.cu1 = Diff / dx / dx; k.cu2 = Diff / dy / dy; k.cu3 = -2.0 * (k.cu1 + k.cu2);
   k.k2n = std::pow(G_K2, G_n); k.krm = std::pow(G_KR, G_m); k.kap = std::pow(G_KA, G_p);
@@ -533,14 +705,14 @@ int crd_rhs_compute(crd_grid *g, double t, const double *y, double *ydot) {
   cudaStream_t st = g->ctx->stream;
   RhsArgs a;
   if (!g->connected) {
-    a = make_args(g, t, y, ydot, 0, g->nyl, y + 2 * (g->nyl - 1) * g->nx, 2, y, 2);
+    a = make_args(g, t, y, ydot, 0, g->nyl, y + 2 * (g->nyl - 1) * g->nx, y);
   } else {
     if (g->epoch == g->computed) { set_error("crd_rhs_compute: no halo posted for this evaluation"); return -1; }
     if (launch_wait(g, st)) return -1;
     HaloLayout L{g->nx};
     const int par = (int)(g->epoch & 1ULL);
-    a = make_args(g, t, y, ydot, 0, g->nyl, (const double *)(g->halo_local + L.ghost_off(par, 0)), 1,
-                  (const double *)(g->halo_local + L.ghost_off(par, 1)), 1);
+    a = make_args(g, t, y, ydot, 0, g->nyl, (const double *)(g->halo_local + L.ghost_off(par, 0)),
+                  (const double *)(g->halo_local + L.ghost_off(par, 1)));
     g->computed = g->epoch;
   }
   if (launch_rhs(g, a, st)) return -1;
@@ -619,7 +791,7 @@ int crd_rhs_host(crd_grid *g, double t, const double *y_host, double *ydot_host)
     const double *south = g->stage_y + 2 * ((r0 == 0 ? nyl : r0) - 1) * nx;
     const double *north = g->stage_y + 2 * (r1 == nyl ? 0 : r1) * nx;
     RhsArgs a = make_args(g, t, g->stage_y, g->stage_ydot, r0, r1, (ghost_s && r0 == 0) ? ghost_s : south,
-                          (ghost_s && r0 == 0) ? 1 : 2, (ghost_n && r1 == nyl) ? ghost_n : north, (ghost_n && r1 == nyl) ? 1 : 2);
+                          (ghost_n && r1 == nyl) ? ghost_n : north);
     if (launch_rhs(g, a, sk)) return -1;
     CRD_CUDA(cudaEventRecord(g->ev_k[c], sk));
     CRD_CUDA(cudaStreamWaitEvent(g->s_out, g->ev_k[c], 0));

@@ -61,9 +61,9 @@ def test_golden_vectors(crd, ctx, oracle):
 
 
 @pytest.mark.parametrize("model", MODELS)
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 10, 11, 12, 13, 14])
 def test_parity_vs_oracle(crd, ctx, oracle, model, variant):
-    for (nx, ny) in ((400, 1600) if variant == 0 else (100, 400), (3, 2), (2, 3), (257, 31), (31, 257)):
+    for (nx, ny) in ((400, 1600) if variant in (0, 10) else (100, 400), (3, 2), (2, 3), (257, 31), (31, 257), (128, 16), (129, 17)):
         for t in (10.0, 50.0):
             P = oracle.make_params(model, nx, ny, t_boundary=38.0)
             y = oracle.fill_state(model, 2 * nx * ny, seed=11 + nx)
@@ -104,6 +104,7 @@ def test_phi_split_is_bitwise_invariant(crd, ctx, oracle):
                 for r in range(nr):
                     js, je = crd.decomp_phi(ny, nr, r)
                     g = crd.Grid(ctx, crd.make_params(model, nx, ny, js=js, je=je, t_boundary=38.0))
+                    g.set_variant(10 if (nr + r) % 2 else 0)      # mix the tiled and the direct kernel
                     grids.append(g)
                     ys.append(crd.NVector.from_numpy(ctx, y[2 * nx * js: 2 * nx * (je + 1)], 2 * nx * ny))
                     ds.append(g.new_vector())
@@ -182,3 +183,29 @@ def test_full_size_properties(crd, ctx):
     crd.N_VLinearSum(1.0, d, -1.0, d2, d)
     assert crd.N_VMaxNorm(d) <= 1e-11 * scale
     g.close(); g2.close()
+
+
+def test_exact_division_edge_values(crd, ctx, oracle):
+    """The EXACT torus stencil divides by 2dx, dx*dx, dy*dy through a reciprocal + two FMA corrections
+    (div_const_rn); zeros (uniform patches, signed), subnormal-range and huge values must take the IEEE
+    fallback and still match the reference bit for bit."""
+    nx, ny = 64, 48
+    base = oracle.fill_state("fhn_torus", 2 * nx * ny, seed=21).reshape(ny, nx, 2)
+    cases = []
+    a = base.copy(); a[10:30, 5:40, :] = 0.0; cases.append(a)                    # exact zeros -> zero numerators
+    a = base.copy(); a[..., 0] = 0.75; cases.append(a)                           # uniform u: all stencil terms are +-0
+    a = base.copy(); a[..., 0] = -0.0; cases.append(a)
+    cases.append(base * 1e-300)                                                  # quotients in the subnormal range
+    cases.append(base * 1e-160)
+    a = base.copy(); a[::2] *= 1e-310; cases.append(a)                           # subnormal inputs next to normal ones
+    cases.append(base * 1e90)                                                    # u^3 ~ 1e270, no overflow
+    for model in ("fhn_torus", "gb_torus"):
+        for k, yy in enumerate(cases):
+            yy = np.ascontiguousarray(yy).ravel()
+            if model == "gb_torus":
+                yy = np.abs(yy)
+            P = oracle.make_params(model, nx, ny, just_diffusion=1 if model == "gb_torus" else 0)
+            ref = oracle.rhs(P, 50.0, yy)
+            for variant in (0, 10):
+                got = gpu_rhs(crd, ctx, model, nx, ny, 50.0, yy, crd.ARITH_EXACT, variant, just_diffusion=1 if model == "gb_torus" else 0)
+                assert got.tobytes() == ref.tobytes(), (model, k, variant)
