@@ -1,0 +1,91 @@
+"""Worker for tests/test_multigpu.py: run under torchrun, one rank per GPU.
+Checks (1) the phi-split RHS over the IPC halo ring is bit-identical to the single-slab CPU checker,
+(2) a multi-rank integration matches the single-rank one within tolerance."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import crdmodel_b200 as crd  # noqa: E402
+from crdmodel_b200 import dist as cdist  # noqa: E402
+import oracle as O  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    ctx = crd.Context(local)
+    ctx.set_comm(rank, world, cdist.make_allreduce())
+    ok = True
+    for model in ("fhn_torus", "gb_torus", "fhn_flat"):
+        nx, ny = 320, 1003
+        y = O.fill_state(model, 2 * nx * ny, seed=17)
+        js, je = crd.decomp_phi(ny, world, rank)
+        for arith in (crd.ARITH_EXACT,):
+            grid = crd.Grid(ctx, crd.make_params(model, nx, ny, js=js, je=je, arith=arith, t_boundary=38.0))
+            cdist.ring_connect(grid, rank, world, cdist.exchange_handles(grid.halo_handle()))
+            yv = crd.NVector.from_numpy(ctx, y[2 * nx * js: 2 * nx * (je + 1)], 2 * nx * ny)
+            dv = grid.new_vector()
+            for t in (10.0, 50.0, 10.0, 50.0, 50.0):      # several epochs through the double-buffered ghosts
+                grid.f(t, yv, dv)
+            got = dv.to_numpy()
+            ref = O.rhs(O.make_params(model, nx, ny, t_boundary=38.0), 50.0, y)[2 * nx * js: 2 * nx * (je + 1)]
+            if model.startswith("fhn"):
+                good = got.tobytes() == ref.tobytes()
+            else:
+                good = bool(np.abs(got - ref).max() <= 1e-12 * (1 + np.abs(ref).max()))
+            # host-buffer entry over the ring
+            out = np.empty_like(got)
+            grid.f_host(50.0, np.ascontiguousarray(y[2 * nx * js: 2 * nx * (je + 1)]), out)
+            good = good and out.tobytes() == got.tobytes()
+            # global reductions
+            nrm = crd.N_VWrmsNorm(yv, yv)
+            want = np.sqrt(np.mean((y * y) ** 2))
+            good = good and abs(nrm - want) <= 1e-12 * want
+            good = good and crd.N_VMaxNorm(yv) == np.abs(y).max() and crd.N_VMin(yv) == y.min()
+            if not good:
+                print("rank %d: FAILED %s" % (rank, model), flush=True)
+            ok = ok and good
+            dist.barrier()
+            ctx.sync()
+            grid.close()
+    # trajectory: phi-split integration == single-slab CPU integration of the same driver
+    nx, ny = 32, 128
+    beta = 1.25
+    js, je = crd.decomp_phi(ny, world, rank)
+    grid = crd.Grid(ctx, crd.make_params("fhn_torus", nx, ny, js=js, je=je, beta=beta, vary_beta=0, t_boundary=1.0))
+    cdist.ring_connect(grid, rank, world, cdist.exchange_handles(grid.halo_handle()))
+    yv = grid.new_vector()
+    grid.fill_initial_conditions(yv, 0.1, 0.5, 1, -beta, beta ** 3 - 3 * beta)
+    solver = crd.ARKodeSolver(grid, yv)
+    flag, t = solver.ARKode(2.0)
+    st = solver.stats()
+    mine = yv.to_numpy()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    full = np.concatenate(gathered)
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_integrate_gpu import cpu_trajectory, reference_ics
+        y0, _ = reference_ics("fhn_torus", nx, ny, beta)
+        cpu, nst_c, nfe_c = cpu_trajectory(O, O.make_params("fhn_torus", nx, ny, beta=beta, vary_beta=0, t_boundary=1.0), y0, [2.0], 1e-5, 1e-10)
+        good = flag == 0 and bool(np.all(np.abs(full - cpu[0]) <= 20 * (1e-5 * np.abs(cpu[0]) + 1e-10)))
+        print("trajectory: world=%d nst=%d nfe=%d (cpu nst=%d) ok=%s" % (world, st["nst"], st["nfe"], nst_c, good), flush=True)
+        ok = ok and good
+    solver.free(); grid.close()
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    if rank == 0:
+        print("MGPU_OK" if all(flags) else "MGPU_FAIL", flush=True)
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(0 if all(flags) else 1)
+
+
+if __name__ == "__main__":
+    main()
