@@ -235,16 +235,15 @@ def main():
     t_wall1 = time.time()
     launches = ctx.launches - launches0
     ms = max_over_ranks(ms)
-    # keep the GPU under the same load a little longer if the timed region was too short to sample clocks
+    # keep the GPU under the same load a little longer if the timed region was too short to sample clocks;
+    # every rank takes the same decision (the halo ring needs all ranks to evaluate the same number of times)
     probe_note = "timed region"
-    if rank == 0 and t_wall1 - t_wall0 < 0.6:
-        probe_note = "timed region + %d further identical launches (region shorter than the 100 ms sampling period x 6)" % 400
+    if max_over_ranks(t_wall1 - t_wall0) < 0.6:
+        probe_note = "timed region + 400 further identical launches (region shorter than the 100 ms sampling period x 6)"
         for _ in range(400):
             grid.f(T_EVAL, y, ydot)
         ctx.sync()
         t_wall1 = time.time()
-    elif use_dist:
-        pass
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     if clocks is not None:
         clocks["sampled_over"] = probe_note
@@ -324,7 +323,7 @@ def main():
                            "parallelism": "phi-split x%d, P2P halo rows over NVLink" % world},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_src,
-                             "kernel": "rhs_kernel<FHN_TORUS,%s,RY=4>" % args.arith, "bytes_per_point": BYTES_PER_POINT,
+                             "kernel": "rhs_tile_kernel<FHN_TORUS,%s,TX=256,TY=16> (TMA bulk-copy tiles)" % args.arith, "bytes_per_point": BYTES_PER_POINT,
                              "points_per_launch": points},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                         "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s / args.e2e_steps,

@@ -76,6 +76,7 @@ SIGNATURES = {
     "crd_f": (I, [D, P, P, P]),
     "crd_grid_rhs_count": (C.c_int64, [P]),
     "crd_grid_set_variant": (I, [P, I]),
+    "crd_grid_set_overlap": (I, [P, I]),
     "crd_fill_synthetic": (I, [P, I, C.c_uint64, C.c_int64, C.c_int64, P]),
     "crd_fill_initial_conditions": (I, [P, C.POINTER(IcParams), P]),
     # device N_Vector

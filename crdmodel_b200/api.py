@@ -231,6 +231,9 @@ class Grid:
     def set_variant(self, v):
         check(lib().crd_grid_set_variant(self._h, v), "crd_grid_set_variant")
 
+    def set_overlap(self, on):
+        check(lib().crd_grid_set_overlap(self._h, 1 if on else 0), "crd_grid_set_overlap")
+
     # f(t, y, ydot, user_data)  — the ARKRhsFn of the reference (FHNmodel_torus.cpp:504)
     def f(self, t, y, ydot):
         check(lib().crd_rhs(self._h, t, _ptr(y), _ptr(ydot)), "crd_rhs")

@@ -72,6 +72,10 @@ struct crd_grid {
   unsigned long long computed = 0;   // epoch of the last compute
   int64_t rhs_count = 0;
   int variant = 0;
+  // overlap of the halo exchange with the interior rows (auxiliary stream)
+  bool overlap = true, split = false;
+  cudaStream_t s_aux = nullptr;
+  cudaEvent_t ev_y = nullptr, ev_b = nullptr;
   // crd_rhs_host staging
   double *stage_y = nullptr, *stage_ydot = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;

@@ -612,6 +612,7 @@ void crd_grid_destroy(crd_grid *g) {
   if (g->stage_y) cudaFree(g->stage_y);
   if (g->stage_ydot) cudaFree(g->stage_ydot);
   if (g->s_in) cudaStreamDestroy(g->s_in);
+  if (g->s_aux) { cudaStreamSynchronize(g->s_aux); cudaStreamDestroy(g->s_aux); cudaEventDestroy(g->ev_y); cudaEventDestroy(g->ev_b); }
   if (g->s_out) cudaStreamDestroy(g->s_out);
   for (int i = 0; i < g->n_chunks; ++i) { cudaEventDestroy(g->ev_in[i]); cudaEventDestroy(g->ev_k[i]); }
   delete[] g->ev_in; delete[] g->ev_k;
@@ -625,6 +626,7 @@ double crd_grid_dx(const crd_grid *g) { return g ? g->dx : 0.0; }
 double crd_grid_dy(const crd_grid *g) { return g ? g->dy : 0.0; }
 int64_t crd_grid_rhs_count(const crd_grid *g) { return g ? g->rhs_count : 0; }
 int crd_grid_set_variant(crd_grid *g, int variant) { if (!g) return -1; g->variant = variant; return 0; }
+int crd_grid_set_overlap(crd_grid *g, int on) { if (!g) return -1; g->overlap = on != 0; return 0; }
 
 int crd_grid_halo_handle(crd_grid *g, unsigned char handle[CRD_HALO_HANDLE_BYTES]) {
   static_assert(sizeof(cudaIpcMemHandle_t) == CRD_HALO_HANDLE_BYTES, "handle size");
@@ -691,31 +693,67 @@ static int launch_wait(crd_grid *g, cudaStream_t st) {
   return check_launch(g->ctx, "halo_wait_kernel");
 }
 
+// Ring evaluation, overlapped: the boundary rows travel on the grid's auxiliary stream while the interior rows
+// (which need no neighbour data) are computed on the main stream.
+//   main: --ev_y--> [ interior rows B .. nyl-B ] ------------------------- wait ev_b --> (caller's next work)
+//   aux : wait ev_y, [push rows 0 / nyl-1 to the neighbours], [wait for theirs], [rows 0..B), [rows nyl-B..nyl), ev_b
+// B = kEdgeRows (a whole number of tile rows).  Slabs too thin to split run everything on the main stream.
+constexpr long long kEdgeRows = 32;
+
+static int ensure_aux(crd_grid *g) {
+  if (g->s_aux) return 0;
+  CRD_CUDA(cudaStreamCreateWithFlags(&g->s_aux, cudaStreamNonBlocking));
+  CRD_CUDA(cudaEventCreateWithFlags(&g->ev_y, cudaEventDisableTiming));
+  CRD_CUDA(cudaEventCreateWithFlags(&g->ev_b, cudaEventDisableTiming));
+  return 0;
+}
+
 int crd_rhs_post_halo(crd_grid *g, const double *y) {
   if (!g || !y) { set_error("crd_rhs_post_halo: null argument"); return -1; }
   if (!g->connected) return 0;  // single rank: the slab wraps onto itself
   if (use(g->ctx)) return -1;
   if (g->epoch != g->computed) { set_error("crd_rhs_post_halo: previous epoch was posted but never computed"); return -1; }
-  return launch_push(g, y, g->ctx->stream);
+  g->split = g->overlap && g->nyl >= 4 * kEdgeRows;
+  if (!g->split) return launch_push(g, y, g->ctx->stream);
+  if (ensure_aux(g)) return -1;
+  CRD_CUDA(cudaEventRecord(g->ev_y, g->ctx->stream));      // y is complete at this point of the main stream
+  CRD_CUDA(cudaStreamWaitEvent(g->s_aux, g->ev_y, 0));
+  return launch_push(g, y, g->s_aux);
 }
 
 int crd_rhs_compute(crd_grid *g, double t, const double *y, double *ydot) {
   if (!g || !y || !ydot) { set_error("crd_rhs_compute: null argument"); return -1; }
   if (use(g->ctx)) return -1;
   cudaStream_t st = g->ctx->stream;
-  RhsArgs a;
   if (!g->connected) {
-    a = make_args(g, t, y, ydot, 0, g->nyl, y + 2 * (g->nyl - 1) * g->nx, y);
-  } else {
-    if (g->epoch == g->computed) { set_error("crd_rhs_compute: no halo posted for this evaluation"); return -1; }
-    if (launch_wait(g, st)) return -1;
-    HaloLayout L{g->nx};
-    const int par = (int)(g->epoch & 1ULL);
-    a = make_args(g, t, y, ydot, 0, g->nyl, (const double *)(g->halo_local + L.ghost_off(par, 0)),
-                  (const double *)(g->halo_local + L.ghost_off(par, 1)));
-    g->computed = g->epoch;
+    RhsArgs a = make_args(g, t, y, ydot, 0, g->nyl, y + 2 * (g->nyl - 1) * g->nx, y);
+    if (launch_rhs(g, a, st)) return -1;
+    g->rhs_count++;
+    return 0;
   }
-  if (launch_rhs(g, a, st)) return -1;
+  if (g->epoch == g->computed) { set_error("crd_rhs_compute: no halo posted for this evaluation"); return -1; }
+  HaloLayout L{g->nx};
+  const int par = (int)(g->epoch & 1ULL);
+  const double *gs = (const double *)(g->halo_local + L.ghost_off(par, 0));
+  const double *gn = (const double *)(g->halo_local + L.ghost_off(par, 1));
+  const long long nx = g->nx, nyl = g->nyl, B = kEdgeRows;
+  if (!g->split) {
+    if (launch_wait(g, st)) return -1;
+    RhsArgs a = make_args(g, t, y, ydot, 0, nyl, gs, gn);
+    if (launch_rhs(g, a, st)) return -1;
+  } else {
+    // interior rows on the main stream: their neighbours are rows of this slab
+    RhsArgs ai = make_args(g, t, y, ydot, B, nyl - B, y + 2 * (B - 1) * nx, y + 2 * (nyl - B) * nx);
+    if (launch_rhs(g, ai, st)) return -1;
+    // edge rows on the auxiliary stream, once the neighbours' rows of this epoch have landed
+    if (launch_wait(g, g->s_aux)) return -1;
+    RhsArgs as = make_args(g, t, y, ydot, 0, B, gs, y + 2 * B * nx);
+    RhsArgs an = make_args(g, t, y, ydot, nyl - B, nyl, y + 2 * (nyl - B - 1) * nx, gn);
+    if (launch_rhs(g, as, g->s_aux) || launch_rhs(g, an, g->s_aux)) return -1;
+    CRD_CUDA(cudaEventRecord(g->ev_b, g->s_aux));
+    CRD_CUDA(cudaStreamWaitEvent(st, g->ev_b, 0));
+  }
+  g->computed = g->epoch;
   g->rhs_count++;
   return 0;
 }

@@ -141,6 +141,8 @@ int crd_f(realtype t, N_Vector y, N_Vector ydot, void *user_data);
 int64_t crd_grid_rhs_count(const crd_grid *g);
 /* kernel variant: 0 = default; others are experimental tilings kept for profiling */
 int crd_grid_set_variant(crd_grid *g, int variant);
+/* on (default): ring evaluations compute the interior rows while the boundary rows are exchanged */
+int crd_grid_set_overlap(crd_grid *g, int on);
 
 /* ---- synthetic states and initial conditions --------------------------------------------------- */
 /* 64-bit LCG stream, element e of the global vector uses state e+1 after `seed`;

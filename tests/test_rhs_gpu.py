@@ -94,12 +94,13 @@ def test_fhn_steady_state_and_constant_field(crd, ctx):
 def test_phi_split_is_bitwise_invariant(crd, ctx, oracle):
     """Emulated ranks on one GPU: all slabs post their halo rows first, then all compute (the push never
     waits, so this order cannot deadlock).  Gathered ydot must equal the single-slab result bit for bit."""
-    for model in MODELS:
-        nx, ny = 96, 203
+    # (96, 203): thin slabs, everything on the main stream; (300, 1100): slabs tall enough for the overlapped
+    # path (interior rows on the main stream, halo + edge rows on the auxiliary stream)
+    for model, nx, ny, ranks in [(m, 96, 203, (1, 2, 3, 8)) for m in MODELS] + [("fhn_torus", 300, 1100, (2, 3)), ("gb_flat", 300, 1100, (2,))]:
         y = oracle.fill_state(model, 2 * nx * ny, seed=5)
         for t in (10.0, 50.0):
             one = gpu_rhs(crd, ctx, model, nx, ny, t, y, crd.ARITH_EXACT, t_boundary=38.0)
-            for nr in (1, 2, 3, 8):
+            for nr in ranks:
                 grids, ys, ds = [], [], []
                 for r in range(nr):
                     js, je = crd.decomp_phi(ny, nr, r)
