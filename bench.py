@@ -48,6 +48,13 @@ class ClockSampler:
 
     def __init__(self, device):
         self.rows, self.proc = [], None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:   # nvidia-smi numbers physical GPUs: map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it is a plain list
+            ids = [int(x) for x in vis.split(",")] if vis else []
+            if device < len(ids):
+                device = ids[device]
+        except ValueError:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)

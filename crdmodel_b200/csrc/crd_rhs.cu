@@ -702,7 +702,11 @@ constexpr long long kEdgeRows = 32;
 
 static int ensure_aux(crd_grid *g) {
   if (g->s_aux) return 0;
-  CRD_CUDA(cudaStreamCreateWithFlags(&g->s_aux, cudaStreamNonBlocking));
+  // highest priority: the few CTAs of push / wait / edge bands must be scheduled as soon as slots free up,
+  // not after the 65k interior CTAs of the main stream have all been dispatched
+  int prio_lo = 0, prio_hi = 0;
+  CRD_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CRD_CUDA(cudaStreamCreateWithPriority(&g->s_aux, cudaStreamNonBlocking, prio_hi));
   CRD_CUDA(cudaEventCreateWithFlags(&g->ev_y, cudaEventDisableTiming));
   CRD_CUDA(cudaEventCreateWithFlags(&g->ev_b, cudaEventDisableTiming));
   return 0;
