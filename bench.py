@@ -136,15 +136,15 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(budget_s=20.0):
+def cpu_baseline(model="fhn_torus", NX=NX, budget_s=20.0):
     """Bounded CPU sample beside the GPU number (rank 0, N = 1): the reference's f() on all host cores."""
     import oracle as O
     cores = os.cpu_count() or 1
-    have_ref = O.ref_available("fhn_torus")
+    have_ref = O.ref_available(model)
     nranks = cores if have_ref else 1
     rows = max(256, 2 * nranks)
-    P = O.make_params("fhn_torus", NX, rows)
-    y = O.fill_state("fhn_torus", 2 * NX * rows)
+    P = O.make_params(model, NX, rows)
+    y = O.fill_state(model, 2 * NX * rows)
     if have_ref:
         _, sec1 = O.ref_rhs(P, T_EVAL, y, nranks=nranks, reps=1, want_out=False)
         reps = int(max(1, min(200, budget_s / max(sec1, 1e-3) / 2)))
@@ -161,8 +161,8 @@ def cpu_baseline(budget_s=20.0):
         single = NX * rows * reps / sec
     return {"value": NX * rows * reps / sec, "unit": UNIT, "cores": nranks, "kind": "reference" if have_ref else "port",
             "single_core_value": single,
-            "sample": "reference f() (oracle/_ref, -O2) on theta %d x phi %d, %d calls, %d emulated MPI ranks on %d host cores"
-                      % (NX, rows, reps, nranks, cores)}
+            "sample": "reference f() of %s (oracle/_ref, -O2) on theta %d x phi %d, %d calls, %d emulated MPI ranks on %d host cores"
+                      % (model, NX, rows, reps, nranks, cores)}
 
 
 def main():
@@ -172,8 +172,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="crd")
     ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
-    ap.add_argument("--rows-per-gpu", type=int, default=ROWS_PER_GPU)
-    ap.add_argument("--nx", type=int, default=NX)
+    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg5"],
+                    help="cfg4: FHN torus 16384 x 16384 per GPU (BASELINE configs[3], the headline); "
+                         "cfg5: Goldbeter torus theta 8192 x 4096 phi rows per GPU (configs[4], global 8192 x 32768 at 8 GPUs)")
+    ap.add_argument("--rows-per-gpu", type=int, default=None)
+    ap.add_argument("--nx", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-integrator", action="store_true")
@@ -213,12 +216,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    nx, nyl = args.nx, args.rows_per_gpu
+    model = "fhn_torus" if args.workload == "cfg4" else "gb_torus"
+    nx = args.nx or (NX if args.workload == "cfg4" else 8192)
+    nyl = args.rows_per_gpu or (ROWS_PER_GPU if args.workload == "cfg4" else 4096)
     ny = nyl * world
     js, je = crd.decomp_phi(ny, world, rank)
     arith = crd.ARITH_EXACT if args.arith == "exact" else crd.ARITH_FAST
     ctx = crd.Context(local_rank)
-    grid = crd.Grid(ctx, crd.make_params("fhn_torus", nx, ny, js=js, je=je, arith=arith))
+    grid = crd.Grid(ctx, crd.make_params(model, nx, ny, js=js, je=je, arith=arith))
     if use_dist:
         ctx.set_comm(rank, world, cdist.make_allreduce(gloo))
         cdist.ring_connect(grid, rank, world, cdist.exchange_handles(grid.halo_handle(), gloo))
@@ -316,21 +321,23 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("rhs_kernel_fhn_torus_%s_%dx%d" % (args.arith, nx, nyl))
+                traffic = json.load(open(tp)).get("rhs_kernel_%s_%s_%dx%d" % (model, args.arith, nx, nyl))
             except Exception:
                 traffic = None
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        metric = METRIC if model == "fhn_torus" else "Goldbeter-torus grid-point RHS evals/sec (fp64)"
+        line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "BASELINE configs[3]: FHN torus RHS f(t,y), synthetic LCG state, theta %d x phi %d per GPU "
-                                       "(global phi %d), phi-split ring of %d GPU(s)" % (nx, nyl, ny, world),
-                           "arith": args.arith + (" (bit-identical to the reference f())" if args.arith == "exact" else " (<=1e-12)"),
+                "config": {"workload": "BASELINE configs[%d]: %s torus RHS f(t,y), synthetic LCG state, theta %d x phi %d per GPU "
+                                       "(global phi %d), phi-split ring of %d GPU(s)" % (3 if model == "fhn_torus" else 4,
+                                                                                       "FHN" if model == "fhn_torus" else "Goldbeter", nx, nyl, ny, world),
+                           "arith": args.arith + ((" (bit-identical to the reference f())" if model == "fhn_torus" else " (reference operation order; libm pow differs by <= a few ulp)") if args.arith == "exact" else " (<=1e-12)"),
                            "nx": nx, "rows_per_gpu": nyl, "ny_global": ny, "t": T_EVAL,
                            "l2": "inputs larger than L2 (%.2f GB per vector vs 126 MB)" % (nbytes / 1e9),
                            "parallelism": "phi-split x%d, P2P halo rows over NVLink" % world},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_src,
-                             "kernel": "rhs_tile_kernel<FHN_TORUS,%s,TX=256,TY=16> (TMA bulk-copy tiles)" % args.arith, "bytes_per_point": BYTES_PER_POINT,
+                             "kernel": "rhs_tile_kernel<%s,%s,TX=256,TY=16> (TMA bulk-copy tiles)" % (model.upper(), args.arith), "bytes_per_point": BYTES_PER_POINT,
                              "points_per_launch": points},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                         "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
@@ -338,7 +345,7 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "integrator": integ}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline()
+                line["cpu_baseline"] = cpu_baseline(model, nx)
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % str(e)[:120]}
         print(json.dumps(line), flush=True)

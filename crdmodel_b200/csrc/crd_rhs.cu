@@ -109,6 +109,24 @@ __device__ __forceinline__ double stencil_exact(const RhsConst &k, double a1, do
   }
 }
 
+// Same sum, but instead of branching per point it ORs "this point needs the IEEE path" into `bad`; the caller
+// redoes the flagged thread's rows afterwards.  Keeps the marched rows free of control flow so they interleave.
+template <int MODEL>
+__device__ __forceinline__ double stencil_exact_acc(const RhsConst &k, double a1, double a3, double uC, double uW,
+                                                    double uE, double uS, double uN, bool &bad) {
+  if (is_torus(MODEL)) {
+    const double two_uC = __dmul_rn(2.0, uC);
+    const double n1 = __dmul_rn(k.Diff, __dmul_rn(a1, __dsub_rn(uE, uW)));
+    const double n2 = __dmul_rn(k.Diff, __dmul_rn(k.inv_rr, __dadd_rn(__dsub_rn(uE, two_uC), uW)));
+    const double n3 = __dmul_rn(k.Diff, __dmul_rn(a3, __dadd_rn(__dsub_rn(uN, two_uC), uS)));
+    bad = bad | div_needs_ieee(n1) | div_needs_ieee(n2) | div_needs_ieee(n3);
+    return __dadd_rn(__dadd_rn(div_const_line(n1, k.twodx, k.r_twodx), div_const_line(n2, k.dxdx, k.r_dxdx)),
+                     div_const_line(n3, k.dydy, k.r_dydy));
+  } else {
+    return stencil_exact<MODEL>(k, a1, a3, uC, uW, uE, uS, uN);
+  }
+}
+
 template <int MODEL>
 __device__ __forceinline__ double stencil_fast(const RhsConst &k, double c1, double c3, double uC, double uW,
                                                double uE, double uS, double uN) {
@@ -228,6 +246,29 @@ __global__ void __launch_bounds__(256, MINB) rhs_kernel(const RhsArgs a) {
   }
 }
 
+// Out-of-line recomputation of one thread's tile column with IEEE divisions (numerators in the subnormal /
+// huge / non-finite range somewhere in the column).  col points at the centre of the thread's first row.
+template <int MODEL>
+__device__ __noinline__ void redo_column_ieee(double Diff, double inv_rr, double twodx, double dxdx, double dydy, double k2n,
+                                              double krm, double kap, int react_on, const double2 *col, int pitch, int nrows,
+                                              double a1, double a3, const double *brow, double2 *out, long long nx) {
+  // scalars by value: taking the address of the kernel parameter block would force every thread to spill it
+  RhsConst k;
+  k.Diff = Diff; k.inv_rr = inv_rr; k.twodx = twodx; k.dxdx = dxdx; k.dydy = dydy; k.k2n = k2n; k.krm = krm; k.kap = kap;
+  for (int r = 0; r < nrows; ++r) {
+    const double2 cc = col[r * pitch];
+    const double uW = col[r * pitch - 1].x, uE = col[r * pitch + 1].x, uS = col[(r - 1) * pitch].x, uN = col[(r + 1) * pitch].x;
+    const double two_uC = __dmul_rn(2.0, cc.x);
+    const double n1 = __dmul_rn(Diff, __dmul_rn(a1, __dsub_rn(uE, uW)));
+    const double n2 = __dmul_rn(Diff, __dmul_rn(inv_rr, __dadd_rn(__dsub_rn(uE, two_uC), uW)));
+    const double n3 = __dmul_rn(Diff, __dmul_rn(a3, __dadd_rn(__dsub_rn(uN, two_uC), uS)));
+    double du = __dadd_rn(__dadd_rn(__ddiv_rn(n1, twodx), __ddiv_rn(n2, dxdx)), __ddiv_rn(n3, dydy));
+    double dv = 0.0;
+    if (react_on) react<MODEL, true>(k, brow[r], cc.x, cc.y, du, dv);
+    out[r * nx] = make_double2(du, dv);
+  }
+}
+
 // ---- the tiled kernel: row segments staged in shared memory by 1-D TMA bulk copies ---------------------
 // One CTA = one tile of TX theta columns x TY phi rows.  An elected thread arms an mbarrier with the tile's
 // byte count and issues one cp.async.bulk (UBLKCP) per tile row: (TX+2) points of rows j0-1 .. j0+TY, the
@@ -242,7 +283,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
-template <int MODEL, bool EXACT, int TX, int TY, int MINB>
+template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC>
 __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   constexpr int PITCH = TX + 2;            // points per staged row (west halo + TX + east halo)
   constexpr int RPT = TY * TX / 256;       // rows marched by one thread
@@ -303,23 +344,18 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   double2 cc = col[0];
   double2 *out = reinterpret_cast<double2 *>(a.ydot) + (j0 + g0) * nx + (i0 + c);
   const int nrows = (h - g0 < RPT) ? (h - g0) : RPT;
-  // frozen rows (t < tBoundary): only slab row 0 / nyl-1 can be one; express them as tile-local row numbers
-  const int fr_s = (a.freeze_south && j0 + g0 == 0) ? 0 : -1;
-  const int fr_n = (a.freeze_north && nyl - 1 - (j0 + g0) < RPT) ? (int)(nyl - 1 - (j0 + g0)) : -1;
   const double *__restrict__ brow = a.brow + (j0 + g0);
   const int react_on = a.react;
+  double2 *const out0 = out;
+  bool bad = (ACC && EXACT && is_torus(MODEL)) ? (a.k.div_safe == 0) : false;
   auto row = [&](int r) {
     const double2 nn = col[(r + 1) * PITCH];
     const double uW = col[r * PITCH - 1].x, uE = col[r * PITCH + 1].x;
-    double du = EXACT ? stencil_exact<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x)
-                      : stencil_fast<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x);
+    double du = !EXACT ? stencil_fast<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x)
+                : ACC  ? stencil_exact_acc<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x, bad)
+                       : stencil_exact<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x);
     double dv = 0.0;
-    if (react_on) {
-      react<MODEL, EXACT>(a.k, __ldg(brow + r), cc.x, cc.y, du, dv);
-      const bool frozen = (r == fr_s) || (r == fr_n);
-      du = frozen ? 0.0 : du;
-      dv = frozen ? 0.0 : dv;
-    }
+    if (react_on) react<MODEL, EXACT>(a.k, __ldg(brow + r), cc.x, cc.y, du, dv);
     *out = make_double2(du, dv);
     out += nx;
     uS = cc.x;
@@ -331,15 +367,25 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   } else {
     for (int r = 0; r < nrows; ++r) row(r);
   }
+  // rare fix-ups, after the marched rows (same thread, same addresses: program order)
+  if (ACC && EXACT && is_torus(MODEL) && bad)
+    redo_column_ieee<MODEL>(a.k.Diff, a.k.inv_rr, a.k.twodx, a.k.dxdx, a.k.dydy, a.k.k2n, a.k.krm, a.k.kap, react_on,
+                            tile + (g0 + 1) * PITCH + (c + 1), PITCH, nrows, t1, t3, brow, out0, nx);
+  if (react_on) {
+    // frozen rows while t < tBoundary (:643-653): only slab row 0 / nyl-1 can be one
+    if (a.freeze_south && j0 + g0 == 0) out0[0] = make_double2(0.0, 0.0);
+    const long long rn = nyl - 1 - (j0 + g0);
+    if (a.freeze_north && rn >= 0 && rn < nrows) out0[rn * nx] = make_double2(0.0, 0.0);
+  }
 }
 
-template <int MODEL, bool EXACT, int TX, int TY, int MINB>
+template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC>
 int launch_tile(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   const long long tiles = ((a.nx + TX - 1) / TX) * ((a.nyl + TY - 1) / TY);
   if (tiles <= 0) return 0;
   if (tiles > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
   const size_t smem = (size_t)(TY + 2) * (TX + 2) * 16 + 16;
-  auto kern = rhs_tile_kernel<MODEL, EXACT, TX, TY, MINB>;
+  auto kern = rhs_tile_kernel<MODEL, EXACT, TX, TY, MINB, ACC>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -352,18 +398,25 @@ int launch_tile(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
 
 template <int MODEL, bool EXACT>
 int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
-  // variant 0 = automatic: the TMA-tiled kernel wherever a tile row is reasonably full, the direct kernel on
-  // narrow meshes (the reference's default 100- and 400-wide grids are L2-resident and launch-bound anyway).
+  // variant 0 = automatic.  Large slabs (>= 4 Mi points, HBM-bound): the TMA-tiled kernel wherever a tile row is
+  // reasonably full.  Small slabs (the reference's default 400x1600 / 100x400 grids live in L2 and are bound by
+  // launch latency and by how many CTAs a partial wave gets): the direct kernel with 2 rows per thread.
   // explicit: direct kernel (rows per thread, min CTAs/SM) 1 (2,4) | 2 (8,2) | 3 (1,4) | 4 (4,3) | 5 (4,4)
   //           tiled kernel (TX, TY, min CTAs/SM) 10 (128,16,4) | 11 (128,32,3) | 12 (64,32,4) | 13 (256,16,3) | 14 (128,16,3)
+  //           15 = 13 with flag-and-redo instead of a branch per point
   int variant = g->variant;
-  if (variant == 0) variant = (a_in.nx >= 192) ? 13 : (a_in.nx >= 96) ? 10 : 5;
+  if (variant == 0) {
+    const long long pts = a_in.nx * a_in.nyl;
+    if (pts < (4LL << 20)) variant = 1;
+    else variant = (a_in.nx >= 192) ? 13 : (a_in.nx >= 96) ? 10 : 5;
+  }
   switch (variant) {
-    case 10: return launch_tile<MODEL, EXACT, 128, 16, 4>(g, a_in, st);
-    case 11: return launch_tile<MODEL, EXACT, 128, 32, 3>(g, a_in, st);
-    case 12: return launch_tile<MODEL, EXACT, 64, 32, 4>(g, a_in, st);
-    case 13: return launch_tile<MODEL, EXACT, 256, 16, 3>(g, a_in, st);
-    case 14: return launch_tile<MODEL, EXACT, 128, 16, 3>(g, a_in, st);
+    case 10: return launch_tile<MODEL, EXACT, 128, 16, 4, false>(g, a_in, st);
+    case 11: return launch_tile<MODEL, EXACT, 128, 32, 3, false>(g, a_in, st);
+    case 12: return launch_tile<MODEL, EXACT, 64, 32, 4, false>(g, a_in, st);
+    case 13: return launch_tile<MODEL, EXACT, 256, 16, 3, false>(g, a_in, st);
+    case 14: return launch_tile<MODEL, EXACT, 128, 16, 3, false>(g, a_in, st);
+    case 15: return launch_tile<MODEL, EXACT, 256, 16, 3, true>(g, a_in, st);   // flag-and-redo instead of a branch per point
     default: break;
   }
   const int RY = (variant == 1) ? 2 : (variant == 2) ? 8 : (variant == 3) ? 1 : 4;

@@ -1,5 +1,7 @@
 """Scratch: a short launch sequence for ncu (FHN / Goldbeter torus, exact / fast, one variant)."""
 import sys
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import crdmodel_b200 as crd
 nx = ny = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0

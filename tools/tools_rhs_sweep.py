@@ -1,7 +1,10 @@
 """Scratch: A/B the RHS kernel variants on the GPU box (sustained runs, interleaved rounds, median)."""
 import sys, json, statistics
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import crdmodel_b200 as crd
-nx = ny = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+nx = int(sys.argv[1].split("x")[0]) if len(sys.argv) > 1 else 16384
+ny = int(sys.argv[1].split("x")[-1]) if len(sys.argv) > 1 else 16384
 variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 10, 11, 13, 14]
 models = sys.argv[3].split(",") if len(sys.argv) > 3 else ["fhn_torus", "gb_torus"]
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 150

@@ -1,6 +1,8 @@
 """Scratch: RHS and integrator throughput on the reference's default (L2-resident, launch-bound) grids and
 the Goldbeter BASELINE config, printed as JSON lines (for profiles/README.md)."""
 import json, sys, time
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import crdmodel_b200 as crd
 ctx = crd.Context(0)
 def rhs_rate(model, nx, ny, arith, reps=300):
