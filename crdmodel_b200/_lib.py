@@ -30,7 +30,7 @@ class IcParams(C.Structure):
 
 
 class FusedOps(C.Structure):
-    _fields_ = [("lincomb", C.c_void_p), ("erk_finish", C.c_void_p)]
+    _fields_ = [("lincomb", C.c_void_p), ("erk_finish", C.c_void_p), ("rhs_lincomb", C.c_void_p)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, c_double_p, C.c_int, C.c_int, C.c_void_p)
@@ -74,6 +74,8 @@ SIGNATURES = {
     "crd_rhs_compute": (I, [P, D, P, P]),
     "crd_rhs_host": (I, [P, D, P, P]),
     "crd_f": (I, [D, P, P, P]),
+    "crd_rhs_lincomb": (I, [P, D, I, c_double_p, C.POINTER(P), P]),
+    "crd_f_lincomb": (I, [D, I, c_double_p, C.POINTER(P), P, P]),
     "crd_grid_rhs_count": (C.c_int64, [P]),
     "crd_grid_set_variant": (I, [P, I]),
     "crd_grid_set_overlap": (I, [P, I]),
@@ -116,6 +118,7 @@ SIGNATURES = {
     "N_VLinearCombination_Crd": (I, [I, c_double_p, C.POINTER(P), P]),
     "N_VErkFinish_Crd": (I, [I, c_double_p, c_double_p, P, C.POINTER(P), P, D, D, c_double_p]),
     "crd_nv_fused_ops": (C.POINTER(FusedOps), []),
+    "crd_nv_fused_vector_ops": (C.POINTER(FusedOps), []),
     # generic dispatchers + ARKode-legacy interface (crd_sundials_compat.h, crd_ark.h)
     "N_VClone": (P, [P]),
     "N_VDestroy": (None, [P]),

@@ -238,6 +238,12 @@ class Grid:
     def f(self, t, y, ydot):
         check(lib().crd_rhs(self._h, t, _ptr(y), _ptr(ydot)), "crd_rhs")
 
+    def f_lincomb(self, t, c, X, ydot):
+        """ydot = f(t, sum_j c[j]*X[j]) without materialising the combination (fused RK stage assembly)."""
+        n = len(c)
+        check(lib().crd_rhs_lincomb(self._h, t, n, (C.c_double * n)(*c), (C.c_void_p * n)(*[_ptr(x) for x in X]), _ptr(ydot)),
+              "crd_rhs_lincomb")
+
     def post_halo(self, y):
         check(lib().crd_rhs_post_halo(self._h, _ptr(y)), "crd_rhs_post_halo")
 
@@ -282,8 +288,11 @@ class ARKodeSolver:
         check(L.ARKodeSStolerances(self.mem, rtol, atol), "ARKodeSStolerances")
         check(L.ARKodeSetUserData(self.mem, grid.handle), "ARKodeSetUserData")
         check(L.ARKodeSetMaxNumSteps(self.mem, max_steps), "ARKodeSetMaxNumSteps")
+        # fused: True / "full" = fused vector ops + stage assembly inside the RHS; "ops" = fused vector ops only;
+        # False = the op-by-op SUNDIALS 2.x sequence
         if fused:
-            check(L.crd_ARKodeSetFusedOps(self.mem, C.cast(L.crd_nv_fused_ops(), C.c_void_p)), "crd_ARKodeSetFusedOps")
+            table = L.crd_nv_fused_vector_ops() if fused == "ops" else L.crd_nv_fused_ops()
+            check(L.crd_ARKodeSetFusedOps(self.mem, C.cast(table, C.c_void_p)), "crd_ARKodeSetFusedOps")
         check(L.crd_ARKodeSetReuseFirstStage(self.mem, 1 if reuse_first_stage else 0), "crd_ARKodeSetReuseFirstStage")
 
     def set_init_step(self, h):

@@ -26,9 +26,25 @@ struct RhsConst {
   double kap;      // pow(KA, p) = 0.6561...
 };
 
+constexpr int kMaxLc = 5;   // yn + up to four stage derivatives (Zonneveld stage 5)
+
+// The state an evaluation reads: a vector y, or (fused stage assembly) the combination sum_j c[j]*x[j]
+// that is never written to memory.
+struct StateRef {
+  const double *y = nullptr;
+  int n = 0;
+  const double *x[kMaxLc] = {};
+  double c[kMaxLc] = {};
+};
+
 struct RhsArgs {
   const double *y;
   double *ydot;
+  // fused stage assembly: nlc >= 1 => state = sum_j lc_c[j]*lc_x[j] (pointers at the launch's first row); y unused
+  int nlc;
+  const double *lc_x[kMaxLc];
+  double lc_c[kMaxLc];
+  long long south_off, north_off;  // nlc >= 1 and south/north == nullptr: point offset of that row inside lc_x
   const double *south;   // the row below the slab's first row (global row js-1), same [nx][2] layout
   const double *north;   // the row above the slab's last row  (global row je+1)
   const double *cth;     // [nx][2]: exact (a1, a3) | fast (c1, c3); unused for flat

@@ -335,7 +335,8 @@ struct _generic_N_Vector_Ops g_ops = {
     N_VDotProd_Crd, N_VMaxNorm_Crd, N_VWrmsNorm_Crd, N_VWrmsNormMask_Crd, N_VMin_Crd, N_VWL2Norm_Crd, N_VL1Norm_Crd,
     N_VCompare_Crd, N_VInvTest_Crd, N_VConstrMask_Crd, N_VMinQuotient_Crd};
 
-const crd_fused_ops g_fused = {N_VLinearCombination_Crd, N_VErkFinish_Crd};
+const crd_fused_ops g_fused = {N_VLinearCombination_Crd, N_VErkFinish_Crd, crd_f_lincomb};
+const crd_fused_ops g_fused_ops_only = {N_VLinearCombination_Crd, N_VErkFinish_Crd, nullptr};
 
 }  // namespace
 
@@ -546,5 +547,6 @@ int N_VErkFinish_Crd(int s, const realtype *hb, const realtype *hd, N_Vector yn,
 }
 
 const crd_fused_ops *crd_nv_fused_ops(void) { return &g_fused; }
+const crd_fused_ops *crd_nv_fused_vector_ops(void) { return &g_fused_ops_only; }
 
 }  // extern "C"

@@ -180,9 +180,42 @@ __device__ __forceinline__ void react(const RhsConst &k, double b, double u, dou
   }
 }
 
+// ---- state access: plain vector, or sum_j c_j x_j formed on the fly (same operation order as lincomb_kernel) ---
+template <bool LC>
+__device__ __forceinline__ double2 state2(const RhsArgs &a, long long p) {
+  if (!LC) return reinterpret_cast<const double2 *>(a.y)[p];
+  double2 v[kMaxLc];
+#pragma unroll
+  for (int j = 0; j < kMaxLc; ++j)
+    v[j] = (j < a.nlc) ? reinterpret_cast<const double2 *>(a.lc_x[j])[p] : make_double2(0.0, 0.0);
+  double2 s = make_double2(a.lc_c[0] * v[0].x, a.lc_c[0] * v[0].y);
+#pragma unroll
+  for (int j = 1; j < kMaxLc; ++j)
+    if (j < a.nlc) { s.x = fma(a.lc_c[j], v[j].x, s.x); s.y = fma(a.lc_c[j], v[j].y, s.y); }
+  return s;
+}
+template <bool LC>
+__device__ __forceinline__ double stateu(const RhsArgs &a, long long p) {
+  if (!LC) return a.y[2 * p];
+  double v[kMaxLc];
+#pragma unroll
+  for (int j = 0; j < kMaxLc; ++j) v[j] = (j < a.nlc) ? a.lc_x[j][2 * p] : 0.0;
+  double s = a.lc_c[0] * v[0];
+#pragma unroll
+  for (int j = 1; j < kMaxLc; ++j)
+    if (j < a.nlc) s = fma(a.lc_c[j], v[j], s);
+  return s;
+}
+// u of the row below / above the launch's rows at column i
+template <bool LC>
+__device__ __forceinline__ double ghost_u(const RhsArgs &a, const double *ptr, long long off, long long i) {
+  if (!LC || ptr) return ptr[2 * i];
+  return stateu<true>(a, off + i);
+}
+
 // ---- the fused kernel ---------------------------------------------------------------------------------
 // work item = (row group jg, column i); rows j0 = jg*RY .. j0+RY-1 of the slab described by `a`.
-template <int MODEL, bool EXACT, int RY, int MINB>
+template <int MODEL, bool EXACT, int RY, int MINB, bool LC>
 __global__ void __launch_bounds__(256, MINB) rhs_kernel(const RhsArgs a) {
   const long long nx = a.nx, nyl = a.nyl;
   const long long w = blockIdx.x * 256LL + threadIdx.x;
@@ -196,9 +229,6 @@ __global__ void __launch_bounds__(256, MINB) rhs_kernel(const RhsArgs a) {
   const long long ie = (i == nx - 1) ? 0 : i + 1;
   const int nrows = (nyl - j0 < RY) ? (int)(nyl - j0) : RY;
 
-  const double2 *__restrict__ y2 = reinterpret_cast<const double2 *>(a.y);
-  const double *__restrict__ y = a.y;
-
   double2 c[RY];
   double uw[RY], ue[RY];
   double uu[RY + 2];  // u of rows j0-1 .. j0+RY
@@ -206,17 +236,17 @@ __global__ void __launch_bounds__(256, MINB) rhs_kernel(const RhsArgs a) {
   for (int r = 0; r < RY; ++r) {
     if (r < nrows) {
       const long long row = (j0 + r) * nx;
-      c[r] = y2[row + i];
-      uw[r] = y[2 * (row + iw)];
-      ue[r] = y[2 * (row + ie)];
+      c[r] = state2<LC>(a, row + i);
+      uw[r] = stateu<LC>(a, row + iw);
+      ue[r] = stateu<LC>(a, row + ie);
     } else {
       c[r] = make_double2(0.0, 0.0); uw[r] = 0.0; ue[r] = 0.0;
     }
   }
-  uu[0] = (j0 == 0) ? a.south[2 * i] : y[2 * ((j0 - 1) * nx + i)];
+  uu[0] = (j0 == 0) ? ghost_u<LC>(a, a.south, a.south_off, i) : stateu<LC>(a, (j0 - 1) * nx + i);
   {
     const long long jn = j0 + nrows;  // row above the last one this thread computes
-    uu[RY + 1] = (jn == nyl) ? a.north[2 * i] : y[2 * (jn * nx + i)];
+    uu[RY + 1] = (jn == nyl) ? ghost_u<LC>(a, a.north, a.north_off, i) : stateu<LC>(a, jn * nx + i);
   }
 #pragma unroll
   for (int r = 0; r < RY; ++r) uu[r + 1] = c[r].x;
@@ -283,7 +313,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
-template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC>
+template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, bool LC>
 __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   constexpr int PITCH = TX + 2;            // points per staged row (west halo + TX + east halo)
   constexpr int RPT = TY * TX / 256;       // rows marched by one thread
@@ -301,6 +331,7 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   const int h = (nyl - j0 < TY) ? (int)(nyl - j0) : TY;          // valid rows of this tile
   const unsigned bar = smem_u32(mbar);
 
+  if (!LC) {
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -320,6 +351,22 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
     }
   }
   __syncthreads();   // barrier initialised before anyone polls it
+  } else {
+    // fused stage assembly: the tile is the combination sum_j c_j x_j, formed while it is staged (the stage
+    // state is never written to HBM); plain coalesced loads, one tile row per pass
+    for (int r = 0; r < h + 2; ++r) {
+      const long long jr = j0 - 1 + r;
+      for (int sc = threadIdx.x; sc < w + 2; sc += 256) {
+        const long long col = (sc == 0) ? (i0 == 0 ? nx - 1 : i0 - 1) : (sc == w + 1) ? (i0 + w == nx ? 0 : i0 + w) : i0 + sc - 1;
+        double2 v;
+        if (jr < 0) v = a.south ? reinterpret_cast<const double2 *>(a.south)[col] : state2<true>(a, a.south_off + col);
+        else if (jr >= nyl) v = a.north ? reinterpret_cast<const double2 *>(a.north)[col] : state2<true>(a, a.north_off + col);
+        else v = state2<true>(a, jr * nx + col);
+        tile[r * PITCH + sc] = v;
+      }
+    }
+    __syncthreads();
+  }
 
   const int c = threadIdx.x % TX;          // column inside the tile
   const int g0 = (threadIdx.x / TX) * RPT; // first tile row of this thread
@@ -330,7 +377,7 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
     t1 = tc.x; t3 = tc.y;
   }
   // wait for the tile (phase 0)
-  {
+  if (!LC) {
     unsigned ok = 0;
     while (!ok) {
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
@@ -379,13 +426,13 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   }
 }
 
-template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC>
-int launch_tile(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, bool LC>
+int launch_tile_lc(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   const long long tiles = ((a.nx + TX - 1) / TX) * ((a.nyl + TY - 1) / TY);
   if (tiles <= 0) return 0;
   if (tiles > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
   const size_t smem = (size_t)(TY + 2) * (TX + 2) * 16 + 16;
-  auto kern = rhs_tile_kernel<MODEL, EXACT, TX, TY, MINB, ACC>;
+  auto kern = rhs_tile_kernel<MODEL, EXACT, TX, TY, MINB, ACC, LC>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -394,6 +441,11 @@ int launch_tile(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   }
   kern<<<(unsigned)tiles, 256, smem, st>>>(a);
   return check_launch(g->ctx, "rhs_tile_kernel");
+}
+template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC>
+int launch_tile(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+  return a.nlc > 0 ? launch_tile_lc<MODEL, EXACT, TX, TY, MINB, ACC, true>(g, a, st)
+                   : launch_tile_lc<MODEL, EXACT, TX, TY, MINB, ACC, false>(g, a, st);
 }
 
 template <int MODEL, bool EXACT>
@@ -434,13 +486,20 @@ int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
   }
   if (blocks > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
   const unsigned nb = (unsigned)blocks;
+  const bool lc = a.nlc > 0;
+#define CRD_DIRECT(RY_, MB_)                                                   \
+  do {                                                                         \
+    if (lc) rhs_kernel<MODEL, EXACT, RY_, MB_, true><<<nb, 256, 0, st>>>(a);   \
+    else rhs_kernel<MODEL, EXACT, RY_, MB_, false><<<nb, 256, 0, st>>>(a);     \
+  } while (0)
   switch (variant) {
-    case 1: rhs_kernel<MODEL, EXACT, 2, 4><<<nb, 256, 0, st>>>(a); break;
-    case 2: rhs_kernel<MODEL, EXACT, 8, 2><<<nb, 256, 0, st>>>(a); break;
-    case 3: rhs_kernel<MODEL, EXACT, 1, 4><<<nb, 256, 0, st>>>(a); break;
-    case 4: rhs_kernel<MODEL, EXACT, 4, 3><<<nb, 256, 0, st>>>(a); break;
-    default: rhs_kernel<MODEL, EXACT, 4, 4><<<nb, 256, 0, st>>>(a); break;
+    case 1: CRD_DIRECT(2, 4); break;
+    case 2: CRD_DIRECT(8, 2); break;
+    case 3: CRD_DIRECT(1, 4); break;
+    case 4: CRD_DIRECT(4, 3); break;
+    default: CRD_DIRECT(4, 4); break;
   }
+#undef CRD_DIRECT
   return check_launch(g->ctx, "rhs_kernel");
 }
 
@@ -456,38 +515,57 @@ int launch_rhs(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   return -1;
 }
 
-// Arguments for rows [r0, r1) of the slab; south/north describe the rows just outside that range.
-RhsArgs make_args(const crd_grid *g, double t, const double *y, double *ydot, long long r0, long long r1,
-                  const double *south, const double *north) {
+// Arguments for rows [r0, r1) of the slab.  The rows just outside that range are given either as an external
+// pointer (ghost row) or as a row index of the slab itself.
+struct RowRef { const double *ptr; long long row; };
+inline RowRef ext_row(const double *p) { return RowRef{p, 0}; }
+inline RowRef slab_row(long long r) { return RowRef{nullptr, r}; }
+
+RhsArgs make_args(const crd_grid *g, double t, const StateRef &S, double *ydot, long long r0, long long r1, RowRef south,
+                  RowRef north) {
   RhsArgs a;
-  a.y = y + 2 * r0 * g->nx;
-  a.ydot = ydot + 2 * r0 * g->nx;
-  a.south = south;
-  a.north = north;
+  const long long nx = g->nx;
+  a.nlc = S.n;
+  a.south_off = a.north_off = 0;
+  if (S.n == 0) {
+    a.y = S.y + 2 * r0 * nx;
+    a.south = south.ptr ? south.ptr : S.y + 2 * south.row * nx;
+    a.north = north.ptr ? north.ptr : S.y + 2 * north.row * nx;
+    for (int j = 0; j < kMaxLc; ++j) { a.lc_x[j] = nullptr; a.lc_c[j] = 0.0; }
+  } else {
+    a.y = nullptr;
+    for (int j = 0; j < kMaxLc; ++j) {
+      a.lc_x[j] = j < S.n ? S.x[j] + 2 * r0 * nx : nullptr;
+      a.lc_c[j] = j < S.n ? S.c[j] : 0.0;
+    }
+    a.south = south.ptr; a.south_off = (south.row - r0) * nx;
+    a.north = north.ptr; a.north_off = (north.row - r0) * nx;
+  }
+  a.ydot = ydot + 2 * r0 * nx;
   a.cth = g->cth;
   a.brow = g->brow + r0;
-  a.nx = g->nx;
+  a.nx = nx;
   a.nyl = r1 - r0;
   const bool tb = t < g->p.t_boundary;
   a.freeze_south = (tb && g->js == 0 && r0 == 0) ? 1 : 0;
   a.freeze_north = (tb && g->je == g->ny - 1 && r1 == g->nyl) ? 1 : 0;
   a.react = (is_fhn(g->p.model) || g->p.just_diffusion == 0) ? 1 : 0;
+  a.div_shift = -1; a.div_magic = 0;
   a.k = g->k;
   return a;
 }
 
 // ---- halo ring: push first/last row into the neighbours' ghost blocks, flag the epoch ------------------
-__global__ void __launch_bounds__(256) halo_push_kernel(const double *__restrict__ y, long long nx, long long nyl,
-                                                        double *prev_north, double *next_south,
+template <bool LC>
+__global__ void __launch_bounds__(256) halo_push_kernel(const RhsArgs a, double *prev_north, double *next_south,
                                                         unsigned long long *prev_flag, unsigned long long *next_flag,
                                                         unsigned long long *ticket, unsigned long long epoch) {
+  const long long nx = a.nx, nyl = a.nyl;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  const double2 *first = reinterpret_cast<const double2 *>(y);
-  const double2 *last = reinterpret_cast<const double2 *>(y + 2 * (nyl - 1) * nx);
   double2 *pn = reinterpret_cast<double2 *>(prev_north), *ns = reinterpret_cast<double2 *>(next_south);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nx; i += stride) {
-    pn[i] = first[i];   // my row js is the row above prev's je
-    ns[i] = last[i];    // my row je is the row below next's js
+    pn[i] = state2<LC>(a, i);                     // my row js is the row above prev's je
+    ns[i] = state2<LC>(a, (nyl - 1) * nx + i);    // my row je is the row below next's js
   }
   __threadfence_system();
   __syncthreads();
@@ -728,14 +806,15 @@ int crd_grid_halo_connect_local(crd_grid *g, crd_grid *prev, crd_grid *next) {
   return 0;
 }
 
-static int launch_push(crd_grid *g, const double *y, cudaStream_t st) {
+static int launch_push(crd_grid *g, const StateRef &S, cudaStream_t st) {
   g->epoch++;
   HaloLayout L{g->nx};
   const int par = (int)(g->epoch & 1ULL);
-  halo_push_kernel<<<kPushBlocks, 256, 0, st>>>(
-      y, g->nx, g->nyl, (double *)(g->halo_prev + L.ghost_off(par, 1)), (double *)(g->halo_next + L.ghost_off(par, 0)),
-      (unsigned long long *)(g->halo_prev + L.flag_off(1)), (unsigned long long *)(g->halo_next + L.flag_off(0)),
-      g->push_ticket, g->epoch);
+  RhsArgs a = make_args(g, 0.0, S, nullptr, 0, g->nyl, slab_row(0), slab_row(0));
+  double *pn = (double *)(g->halo_prev + L.ghost_off(par, 1)), *ns = (double *)(g->halo_next + L.ghost_off(par, 0));
+  unsigned long long *pf = (unsigned long long *)(g->halo_prev + L.flag_off(1)), *nf = (unsigned long long *)(g->halo_next + L.flag_off(0));
+  if (S.n > 0) halo_push_kernel<true><<<kPushBlocks, 256, 0, st>>>(a, pn, ns, pf, nf, g->push_ticket, g->epoch);
+  else halo_push_kernel<false><<<kPushBlocks, 256, 0, st>>>(a, pn, ns, pf, nf, g->push_ticket, g->epoch);
   return check_launch(g->ctx, "halo_push_kernel");
 }
 
@@ -765,25 +844,22 @@ static int ensure_aux(crd_grid *g) {
   return 0;
 }
 
-int crd_rhs_post_halo(crd_grid *g, const double *y) {
-  if (!g || !y) { set_error("crd_rhs_post_halo: null argument"); return -1; }
+static int post_state(crd_grid *g, const StateRef &S) {
   if (!g->connected) return 0;  // single rank: the slab wraps onto itself
-  if (use(g->ctx)) return -1;
   if (g->epoch != g->computed) { set_error("crd_rhs_post_halo: previous epoch was posted but never computed"); return -1; }
   g->split = g->overlap && g->nyl >= 4 * kEdgeRows;
-  if (!g->split) return launch_push(g, y, g->ctx->stream);
+  if (!g->split) return launch_push(g, S, g->ctx->stream);
   if (ensure_aux(g)) return -1;
-  CRD_CUDA(cudaEventRecord(g->ev_y, g->ctx->stream));      // y is complete at this point of the main stream
+  CRD_CUDA(cudaEventRecord(g->ev_y, g->ctx->stream));      // the state is complete at this point of the main stream
   CRD_CUDA(cudaStreamWaitEvent(g->s_aux, g->ev_y, 0));
-  return launch_push(g, y, g->s_aux);
+  return launch_push(g, S, g->s_aux);
 }
 
-int crd_rhs_compute(crd_grid *g, double t, const double *y, double *ydot) {
-  if (!g || !y || !ydot) { set_error("crd_rhs_compute: null argument"); return -1; }
-  if (use(g->ctx)) return -1;
+static int compute_state(crd_grid *g, double t, const StateRef &S, double *ydot) {
   cudaStream_t st = g->ctx->stream;
+  const long long nyl = g->nyl, B = kEdgeRows;
   if (!g->connected) {
-    RhsArgs a = make_args(g, t, y, ydot, 0, g->nyl, y + 2 * (g->nyl - 1) * g->nx, y);
+    RhsArgs a = make_args(g, t, S, ydot, 0, nyl, slab_row(nyl - 1), slab_row(0));
     if (launch_rhs(g, a, st)) return -1;
     g->rhs_count++;
     return 0;
@@ -793,19 +869,18 @@ int crd_rhs_compute(crd_grid *g, double t, const double *y, double *ydot) {
   const int par = (int)(g->epoch & 1ULL);
   const double *gs = (const double *)(g->halo_local + L.ghost_off(par, 0));
   const double *gn = (const double *)(g->halo_local + L.ghost_off(par, 1));
-  const long long nx = g->nx, nyl = g->nyl, B = kEdgeRows;
   if (!g->split) {
     if (launch_wait(g, st)) return -1;
-    RhsArgs a = make_args(g, t, y, ydot, 0, nyl, gs, gn);
+    RhsArgs a = make_args(g, t, S, ydot, 0, nyl, ext_row(gs), ext_row(gn));
     if (launch_rhs(g, a, st)) return -1;
   } else {
     // interior rows on the main stream: their neighbours are rows of this slab
-    RhsArgs ai = make_args(g, t, y, ydot, B, nyl - B, y + 2 * (B - 1) * nx, y + 2 * (nyl - B) * nx);
+    RhsArgs ai = make_args(g, t, S, ydot, B, nyl - B, slab_row(B - 1), slab_row(nyl - B));
     if (launch_rhs(g, ai, st)) return -1;
     // edge rows on the auxiliary stream, once the neighbours' rows of this epoch have landed
     if (launch_wait(g, g->s_aux)) return -1;
-    RhsArgs as = make_args(g, t, y, ydot, 0, B, gs, y + 2 * B * nx);
-    RhsArgs an = make_args(g, t, y, ydot, nyl - B, nyl, y + 2 * (nyl - B - 1) * nx, gn);
+    RhsArgs as = make_args(g, t, S, ydot, 0, B, ext_row(gs), slab_row(B));
+    RhsArgs an = make_args(g, t, S, ydot, nyl - B, nyl, slab_row(nyl - B - 1), ext_row(gn));
     if (launch_rhs(g, as, g->s_aux) || launch_rhs(g, an, g->s_aux)) return -1;
     CRD_CUDA(cudaEventRecord(g->ev_b, g->s_aux));
     CRD_CUDA(cudaStreamWaitEvent(st, g->ev_b, 0));
@@ -815,9 +890,49 @@ int crd_rhs_compute(crd_grid *g, double t, const double *y, double *ydot) {
   return 0;
 }
 
+static StateRef plain_state(const double *y) { StateRef S; S.y = y; S.n = 0; return S; }
+
+int crd_rhs_post_halo(crd_grid *g, const double *y) {
+  if (!g || !y) { set_error("crd_rhs_post_halo: null argument"); return -1; }
+  if (use(g->ctx)) return -1;
+  return post_state(g, plain_state(y));
+}
+
+int crd_rhs_compute(crd_grid *g, double t, const double *y, double *ydot) {
+  if (!g || !y || !ydot) { set_error("crd_rhs_compute: null argument"); return -1; }
+  if (use(g->ctx)) return -1;
+  return compute_state(g, t, plain_state(y), ydot);
+}
+
 int crd_rhs(crd_grid *g, double t, const double *y, double *ydot) {
   if (crd_rhs_post_halo(g, y)) return -1;
   return crd_rhs_compute(g, t, y, ydot);
+}
+
+// ydot = f(t, sum_j c[j]*X[j]) without materialising the combination (explicit RK stage assembly fused into the
+// evaluation).  n <= 5; the vectors must not alias ydot.
+int crd_rhs_lincomb(crd_grid *g, double t, int n, const double *c, const double *const *X_dev, double *ydot) {
+  if (!g || !c || !X_dev || !ydot || n < 1 || n > kMaxLc) { set_error("crd_rhs_lincomb: bad arguments"); return -1; }
+  if (use(g->ctx)) return -1;
+  StateRef S;
+  S.n = n;
+  for (int j = 0; j < n; ++j) {
+    if (!X_dev[j] || X_dev[j] == ydot) { set_error("crd_rhs_lincomb: null or aliased vector"); return -1; }
+    S.x[j] = X_dev[j]; S.c[j] = c[j];
+  }
+  if (post_state(g, S)) return -1;
+  return compute_state(g, t, S, ydot);
+}
+
+int crd_f_lincomb(realtype t, int n, const realtype *c, N_Vector *X, N_Vector ydot, void *user_data) {
+  crd_grid *g = (crd_grid *)user_data;
+  if (!g || !X || !ydot || n < 1 || n > kMaxLc) return -1;
+  const double *xs[kMaxLc];
+  for (int j = 0; j < n; ++j) {
+    xs[j] = N_VGetDeviceArrayPointer_Crd(X[j]);
+    if (!xs[j] || N_VGetLocalLength_Crd(X[j]) != crd_grid_local_length(g)) { set_error("crd_f_lincomb: vector does not match the grid"); return -1; }
+  }
+  return crd_rhs_lincomb(g, t, n, c, xs, N_VGetDeviceArrayPointer_Crd(ydot)) == 0 ? 0 : -1;
 }
 
 int crd_f(realtype t, N_Vector y, N_Vector ydot, void *user_data) {
@@ -866,7 +981,7 @@ int crd_rhs_host(crd_grid *g, double t, const double *y_host, double *ydot_host)
     CRD_CUDA(cudaMemcpyAsync(g->stage_y, y_host, row_bytes, cudaMemcpyHostToDevice, g->s_in));
     CRD_CUDA(cudaEventRecord(g->ev_k[0], g->s_in));
     CRD_CUDA(cudaStreamWaitEvent(sk, g->ev_k[0], 0));
-    if (launch_push(g, g->stage_y, sk)) return -1;
+    if (launch_push(g, plain_state(g->stage_y), sk)) return -1;
     if (launch_wait(g, sk)) return -1;
     HaloLayout L{g->nx};
     const int par = (int)(g->epoch & 1ULL);
@@ -883,10 +998,9 @@ int crd_rhs_host(crd_grid *g, double t, const double *y_host, double *ydot_host)
     const long long r0 = r_begin(c), r1 = r_begin(c + 1);
     if (r1 == r0) continue;
     CRD_CUDA(cudaStreamWaitEvent(sk, g->ev_in[c + 1 < C ? c + 1 : c], 0));
-    const double *south = g->stage_y + 2 * ((r0 == 0 ? nyl : r0) - 1) * nx;
-    const double *north = g->stage_y + 2 * (r1 == nyl ? 0 : r1) * nx;
-    RhsArgs a = make_args(g, t, g->stage_y, g->stage_ydot, r0, r1, (ghost_s && r0 == 0) ? ghost_s : south,
-                          (ghost_n && r1 == nyl) ? ghost_n : north);
+    const RowRef south = (ghost_s && r0 == 0) ? ext_row(ghost_s) : slab_row((r0 == 0 ? nyl : r0) - 1);
+    const RowRef north = (ghost_n && r1 == nyl) ? ext_row(ghost_n) : slab_row(r1 == nyl ? 0 : r1);
+    RhsArgs a = make_args(g, t, plain_state(g->stage_y), g->stage_ydot, r0, r1, south, north);
     if (launch_rhs(g, a, sk)) return -1;
     CRD_CUDA(cudaEventRecord(g->ev_k[c], sk));
     CRD_CUDA(cudaStreamWaitEvent(g->s_out, g->ev_k[c], 0));

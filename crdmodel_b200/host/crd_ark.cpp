@@ -235,14 +235,30 @@ int take_step(ArkMem *m) {
         m->Fp[0] = m->fnew;  // f(tn, yn), evaluated when the previous step completed
         continue;
       }
-      N_Vector ystage = m->yn;
-      if (is > 0) {
-        double coef[S_MAX];
-        for (int j = 0; j < is; ++j) coef[j] = m->h * m->A[is][j];
-        if (assemble(m, m->yn, is, coef, m->Fp, m->ycur) != 0) return ARK_MEM_FAIL;
-        ystage = m->ycur;
+      int r;
+      if (is > 0 && m->fused && m->fused->rhs_lincomb) {
+        // stage state yn + h sum_j A_ij F_j formed inside the evaluation (zero coefficients dropped)
+        double cc[S_MAX + 1];
+        N_Vector XX[S_MAX + 1];
+        int n = 0;
+        cc[n] = 1.0; XX[n++] = m->yn;
+        for (int j = 0; j < is; ++j)
+          if (m->A[is][j] != 0.0) { cc[n] = m->h * m->A[is][j]; XX[n++] = m->Fp[j]; }
+        r = m->fused->rhs_lincomb(m->tn + m->c[is] * m->h, n, cc, XX, m->Fp[is], m->user_data);
+        m->nfe++;
+      } else {
+        N_Vector ystage = m->yn;
+        if (is > 0) {
+          double coef[S_MAX];
+          N_Vector Xs[S_MAX];
+          int n = 0;
+          for (int j = 0; j < is; ++j)
+            if (m->A[is][j] != 0.0) { coef[n] = m->h * m->A[is][j]; Xs[n++] = m->Fp[j]; }
+          if (assemble(m, m->yn, n, coef, Xs, m->ycur) != 0) return ARK_MEM_FAIL;
+          ystage = m->ycur;
+        }
+        r = rhs(m, m->tn + m->c[is] * m->h, ystage, m->Fp[is]);
       }
-      int r = rhs(m, m->tn + m->c[is] * m->h, ystage, m->Fp[is]);
       if (r < 0) return ARK_RHSFUNC_FAIL;
       if (r > 0) {  // recoverable: shrink and retry (etacf = 0.25)
         if (++ncf == m->maxncf || m->hfixed != 0.0) return ARK_REPTD_RHSFUNC_ERR;

@@ -137,6 +137,10 @@ int crd_rhs_host(crd_grid *g, double t, const double *y_host, double *ydot_host)
 /* ARKRhsFn: user_data is the crd_grid*, y and ydot are device N_Vectors (N_VNew_Crd).  Returns 0,
  * or -1 if the evaluation could not be issued (the reference returns -1 when Exchange fails, :522). */
 int crd_f(realtype t, N_Vector y, N_Vector ydot, void *user_data);
+/* ydot = f(t, sum_j c[j]*X[j]), n <= 5, without materialising the combination: the explicit RK stage assembly
+ * (ARKode's N_VLinearSum chain before each stage, inside ARKode() :423) fused into the evaluation. */
+int crd_rhs_lincomb(crd_grid *g, double t, int n, const double *c, const double *const *X_dev, double *ydot_dev);
+int crd_f_lincomb(realtype t, int n, const realtype *c, N_Vector *X, N_Vector ydot, void *user_data);
 /* count of RHS evaluations issued on this grid */
 int64_t crd_grid_rhs_count(const crd_grid *g);
 /* kernel variant: 0 = default; others are experimental tilings kept for profiling */
@@ -203,7 +207,8 @@ realtype N_VMinQuotient_Crd(N_Vector num, N_Vector denom);
 int N_VLinearCombination_Crd(int n, const realtype *c, N_Vector *X, N_Vector z);
 int N_VErkFinish_Crd(int s, const realtype *hb, const realtype *hd, N_Vector yn, N_Vector *F, N_Vector ynew,
                      realtype rtol, realtype atol, realtype out[2]);
-const crd_fused_ops *crd_nv_fused_ops(void);
+const crd_fused_ops *crd_nv_fused_ops(void);        /* lincomb + erk_finish + rhs_lincomb */
+const crd_fused_ops *crd_nv_fused_vector_ops(void); /* lincomb + erk_finish only (stage states are materialised) */
 
 #ifdef __cplusplus
 }

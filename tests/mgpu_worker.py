@@ -39,6 +39,14 @@ def main():
                 good = got.tobytes() == ref.tobytes()
             else:
                 good = bool(np.abs(got - ref).max() <= 1e-12 * (1 + np.abs(ref).max()))
+            # fused stage assembly over the ring: f(t, sum c_j X_j) == lincomb then f, bit for bit
+            X2 = O.fill_state(model, 2 * nx * ny, seed=18)
+            xv = crd.NVector.from_numpy(ctx, X2[2 * nx * js: 2 * nx * (je + 1)], 2 * nx * ny)
+            zv, d1, d2 = grid.new_vector(), grid.new_vector(), grid.new_vector()
+            crd.N_VLinearCombination([1.0, 0.01], [yv, xv], zv)
+            grid.f(50.0, zv, d1)
+            grid.f_lincomb(50.0, [1.0, 0.01], [yv, xv], d2)
+            good = good and d1.to_numpy().tobytes() == d2.to_numpy().tobytes()
             # host-buffer entry over the ring
             out = np.empty_like(got)
             grid.f_host(50.0, np.ascontiguousarray(y[2 * nx * js: 2 * nx * (je + 1)]), out)

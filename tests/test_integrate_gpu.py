@@ -98,3 +98,22 @@ def test_reuse_first_stage_is_bitwise_neutral(crd, ctx):
         s.free(); grid.close()
     assert res[0][0].tobytes() == res[1][0].tobytes()
     assert res[0][1]["nst"] == res[1][1]["nst"] and res[1][1]["nfe"] < res[0][1]["nfe"]
+
+
+def test_fused_stage_rhs_does_not_change_the_trajectory(crd, ctx):
+    """fused="full" (stage assembly inside the RHS kernel) and fused="ops" (stage states materialised by
+    lincomb_kernel) run the same arithmetic: identical bits, identical counters, fewer kernel launches."""
+    nx, ny = 48, 192
+    y0, _ = reference_ics("fhn_torus", nx, ny, 1.25)
+    res = []
+    for mode in ("ops", "full"):
+        grid = crd.Grid(ctx, crd.make_params("fhn_torus", nx, ny, beta=1.25, vary_beta=0, t_boundary=0.5))
+        y = crd.NVector.from_numpy(ctx, y0)
+        l0 = ctx.launches
+        s = crd.ARKodeSolver(grid, y, fused=mode)
+        assert s.ARKode(1.5)[0] == 0
+        res.append((y.to_numpy(), s.stats(), ctx.launches - l0))
+        s.free(); grid.close()
+    assert res[0][0].tobytes() == res[1][0].tobytes()
+    assert res[0][1]["nst"] == res[1][1]["nst"] and res[0][1]["nfe"] == res[1][1]["nfe"]
+    assert res[1][2] < res[0][2]

@@ -210,3 +210,25 @@ def test_exact_division_edge_values(crd, ctx, oracle):
             for variant in (0, 10):
                 got = gpu_rhs(crd, ctx, model, nx, ny, 50.0, yy, crd.ARITH_EXACT, variant, just_diffusion=1 if model == "gb_torus" else 0)
                 assert got.tobytes() == ref.tobytes(), (model, k, variant)
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_fused_stage_rhs_equals_lincomb_then_rhs(crd, ctx, oracle, model):
+    """crd_rhs_lincomb: f(t, sum c_j X_j) with the stage state formed inside the kernel must give the bits of
+    N_VLinearCombination followed by f — every kernel (tiled / direct), single slab and the emulated ring."""
+    rng = np.random.default_rng(3)
+    for (nx, ny) in ((300, 700), (64, 37), (2, 3)):
+        n_el = 2 * nx * ny
+        X = [oracle.fill_state(model, n_el, seed=40 + j) for j in range(5)]
+        for ncomb, coefs in ((1, [1.0]), (2, [1.0, 0.013]), (3, [1.0, 0.02, -0.007]), (5, [1.0, 0.004, 0.005, 0.009, -0.001])):
+            for variant in (0, 1, 5, 10, 13):
+                g = crd.Grid(ctx, crd.make_params(model, nx, ny, t_boundary=38.0))
+                g.set_variant(variant)
+                V = [crd.NVector.from_numpy(ctx, x) for x in X[:ncomb]]
+                z, d1, d2 = g.new_vector(), g.new_vector(), g.new_vector()
+                crd.N_VLinearCombination(coefs, V, z)
+                for t in (10.0, 50.0):
+                    g.f(t, z, d1)
+                    g.f_lincomb(t, coefs, V, d2)
+                    assert d1.to_numpy().tobytes() == d2.to_numpy().tobytes(), (model, nx, ny, ncomb, variant, t)
+                g.close()
