@@ -353,18 +353,46 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   __syncthreads();   // barrier initialised before anyone polls it
   } else {
     // fused stage assembly: the tile is the combination sum_j c_j x_j, formed while it is staged (the stage
-    // state is never written to HBM); plain coalesced loads, one tile row per pass
-    for (int r = 0; r < h + 2; ++r) {
+    // state is never written to HBM).  Plain coalesced 16-byte loads; each thread stages its own column, four
+    // rows per pass so that 4 loads per input vector are in flight, then the few halo-column entries.
+    auto generic = [&](int r, int sc) {
       const long long jr = j0 - 1 + r;
-      for (int sc = threadIdx.x; sc < w + 2; sc += 256) {
-        const long long col = (sc == 0) ? (i0 == 0 ? nx - 1 : i0 - 1) : (sc == w + 1) ? (i0 + w == nx ? 0 : i0 + w) : i0 + sc - 1;
-        double2 v;
-        if (jr < 0) v = a.south ? reinterpret_cast<const double2 *>(a.south)[col] : state2<true>(a, a.south_off + col);
-        else if (jr >= nyl) v = a.north ? reinterpret_cast<const double2 *>(a.north)[col] : state2<true>(a, a.north_off + col);
-        else v = state2<true>(a, jr * nx + col);
-        tile[r * PITCH + sc] = v;
+      const long long col = (sc == 0) ? (i0 == 0 ? nx - 1 : i0 - 1) : (sc == w + 1) ? (i0 + w == nx ? 0 : i0 + w) : i0 + sc - 1;
+      double2 v;
+      if (jr < 0) v = a.south ? reinterpret_cast<const double2 *>(a.south)[col] : state2<true>(a, a.south_off + col);
+      else if (jr >= nyl) v = a.north ? reinterpret_cast<const double2 *>(a.north)[col] : state2<true>(a, a.north_off + col);
+      else v = state2<true>(a, jr * nx + col);
+      tile[r * PITCH + sc] = v;
+    };
+    const int r_lo = (j0 == 0) ? 1 : 0, r_hi = (j0 + h == nyl) ? h + 1 : h + 2;   // tile rows that are rows of this launch
+    constexpr int R = 4;
+    for (int tcol = threadIdx.x; tcol < w; tcol += 256) {
+      const long long p0 = (j0 - 1) * nx + i0 + tcol;   // point offset of tile row 0 in this column
+      for (int rb = r_lo; rb < r_hi; rb += R) {
+        double2 acc[R], v[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+          v[rr] = (rb + rr < r_hi) ? reinterpret_cast<const double2 *>(a.lc_x[0])[p0 + (rb + rr) * nx] : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) acc[rr] = make_double2(a.lc_c[0] * v[rr].x, a.lc_c[0] * v[rr].y);
+#pragma unroll
+        for (int j = 1; j < kMaxLc; ++j) {
+          if (j < a.nlc) {
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+              v[rr] = (rb + rr < r_hi) ? reinterpret_cast<const double2 *>(a.lc_x[j])[p0 + (rb + rr) * nx] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) { acc[rr].x = fma(a.lc_c[j], v[rr].x, acc[rr].x); acc[rr].y = fma(a.lc_c[j], v[rr].y, acc[rr].y); }
+          }
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+          if (rb + rr < r_hi) tile[(rb + rr) * PITCH + tcol + 1] = acc[rr];
       }
+      if (r_lo == 1) generic(0, tcol + 1);          // ghost row below the slab
+      if (r_hi == h + 1) generic(h + 1, tcol + 1);  // ghost row above the slab
     }
+    for (int e = threadIdx.x; e < 2 * (h + 2); e += 256) generic(e >> 1, (e & 1) ? w + 1 : 0);   // halo columns
     __syncthreads();
   }
 
