@@ -15,6 +15,7 @@ struct RhsConst {
   double dxdx;     // dx*dx
   double dydy;     // dy*dy
   double r_twodx, r_dxdx, r_dydy;  // RN(1/x) of the three divisors (host IEEE division)
+  int dv_plus0;    // some beta(phi) is -0.0: keep the reference's 0.0 + eps*(u+b)
   int div_safe;    // divisors positive and within 2^+-90: the reciprocal-refinement division applies
   // torus, fast: folded
   double c2;       // Diff*inv_rr/dxdx

@@ -86,6 +86,15 @@ __device__ __noinline__ double stencil_sum_ieee(double n1, double n2, double n3,
   return __dadd_rn(__dadd_rn(__ddiv_rn(n1, c1), __ddiv_rn(n2, c2)), __ddiv_rn(n3, c3));
 }
 
+// all three numerators at once: min / max of the high words decide the common case in 8 integer instructions
+__device__ __forceinline__ bool div3_needs_ieee(double n1, double n2, double n3) {
+  const unsigned t1 = (unsigned)__double2hiint(n1) & 0x7fffffffu, t2 = (unsigned)__double2hiint(n2) & 0x7fffffffu,
+                 t3 = (unsigned)__double2hiint(n3) & 0x7fffffffu;
+  const unsigned mn = min(t1, min(t2, t3)), mx = max(t1, max(t2, t3));
+  if (mn >= 0x0DF00000u && mx < 0x71F00000u) return false;        // every |n| in [2^-800, 2^800)
+  return div_needs_ieee(n1) || div_needs_ieee(n2) || div_needs_ieee(n3);   // zeros are fine, the rest is not
+}
+
 // EXACT: the reference's expression tree with separately rounded operations.
 template <int MODEL>
 __device__ __forceinline__ double stencil_exact(const RhsConst &k, double a1, double a3, double uC, double uW,
@@ -99,7 +108,7 @@ __device__ __forceinline__ double stencil_exact(const RhsConst &k, double a1, do
     double T1 = div_const_line(n1, k.twodx, k.r_twodx);
     double T2 = div_const_line(n2, k.dxdx, k.r_dxdx);
     double T3 = div_const_line(n3, k.dydy, k.r_dydy);
-    if (!k.div_safe || div_needs_ieee(n1) || div_needs_ieee(n2) || div_needs_ieee(n3))
+    if (!k.div_safe || div3_needs_ieee(n1, n2, n3))
       return stencil_sum_ieee(n1, n2, n3, k.twodx, k.dxdx, k.dydy);  // tiny / huge / non-finite numerator: rare, out of line
     return __dadd_rn(__dadd_rn(T1, T2), T3);
   } else {
@@ -152,7 +161,9 @@ __device__ __forceinline__ void react(const RhsConst &k, double b, double u, dou
     if (EXACT) {
       // :657  ydot_u += 3u - u*u*u - v      :660  ydot_v += EPSILON*(u + b)
       du = __dadd_rn(du, __dsub_rn(__dsub_rn(__dmul_rn(3.0, u), __dmul_rn(__dmul_rn(u, u), u)), v));
-      dv = __dadd_rn(0.0, __dmul_rn(kEps, __dadd_rn(u, b)));
+      // ydot_v starts at 0.0 (N_VConst :506): 0.0 + x differs from x only for x = -0, i.e. u = b = -0
+      dv = __dmul_rn(kEps, __dadd_rn(u, b));
+      if (k.dv_plus0) dv = __dadd_rn(0.0, dv);
     } else {
       du += (3.0 * u - u * u * u) - v;
       dv = kEps * (u + b);
@@ -167,7 +178,7 @@ __device__ __forceinline__ void react(const RhsConst &k, double b, double u, dou
       const double v3 = __ddiv_rn(__dmul_rn(__dmul_rn(G_VM3, y2), z4),
                                   __dmul_rn(__dadd_rn(k.krm, y2), __dadd_rn(k.kap, z4)));
       du = __dadd_rn(du, __dsub_rn(__dadd_rn(__dadd_rn(__dsub_rn(b, v2), v3), __dmul_rn(G_kf, Y)), __dmul_rn(G_k, Z)));
-      dv = __dadd_rn(0.0, __dsub_rn(__dsub_rn(v2, v3), __dmul_rn(G_kf, Y)));
+      dv = __dsub_rn(__dsub_rn(v2, v3), __dmul_rn(G_kf, Y));   // never -0 (v2 - v3 is +0 when it vanishes), so 0.0 + dv == dv
     } else {
       // w = v2 - v3 = A/B - C/D with one reciprocal: (A*D - C*B) / (B*D)
       const double z2 = Z * Z, y2 = Y * Y, z4 = z2 * z2;
@@ -716,6 +727,7 @@ crd_grid *crd_grid_create(crd_ctx *ctx, const crd_params *p) {
   }
   k.c2 = torus ? Diff * k.inv_rr / k.dxdx : 0.0;
   k.cu1 = Diff / dx / dx; k.cu2 = Diff / dy / dy; k.cu3 = -2.0 * (k.cu1 + k.cu2);
+  k.dv_plus0 = 0;
   k.k2n = std::pow(G_K2, G_n); k.krm = std::pow(G_KR, G_m); k.kap = std::pow(G_KA, G_p);
 
   // per-theta metric table (host libm, the reference's expressions :531-537)
@@ -738,6 +750,7 @@ crd_grid *crd_grid_create(crd_ctx *ctx, const crd_params *p) {
     const bool vary = fhn ? (p->vary_beta != 0) : (p->vary_beta == 1);
     if (vary) b = p->beta_min + yy * (p->beta_max - p->beta_min) / (g->ymax - g->ymin);
     brow[j] = fhn ? b : (G_v0 + G_v1 * b);
+    if (fhn && b == 0.0 && std::signbit(b)) k.dv_plus0 = 1;
   }
   cudaError_t e;
   if ((e = cudaMalloc(&g->cth, cth.size() * sizeof(double))) != cudaSuccess ||

@@ -29,6 +29,7 @@
 
 #include "crd_b200.h"
 #include "crd_ini.hpp"
+#include "crd_writer.hpp"
 
 #ifndef CRD_DRIVER_MODEL
 #define CRD_DRIVER_MODEL 0
@@ -335,16 +336,11 @@ int run(const Config &c, int rank, int nranks) {
   FILE *UFID2 = fopen(outname, "w");
   if (!UFID || !UFID2) { cerr << "cannot open output files\n"; return 1; }
 
-  std::vector<char> line;
+  // output off the critical path: snapshot -> background thread formats with all host cores -> ordered write
+  crd::AsyncWriter writer(UFID, UFID2, c.INCLUDE_ALL_VARS == 1, nxl * nyl);
   auto write_state = [&]() -> int {
     if (N_VCopyToHost_Crd(y) != 0) { cerr << crd_last_error() << "\n"; return 1; }
-    for (int var = 0; var < (c.INCLUDE_ALL_VARS == 1 ? 2 : 1); ++var) {
-      line.resize((size_t)nxl * nyl * 25 + 2);
-      size_t pos = 0;
-      for (long k = 0; k < nxl * nyl; ++k) pos += (size_t)snprintf(&line[pos], 26, " %.16e", ydata[2 * k + var]);
-      line[pos++] = '\n';
-      fwrite(line.data(), 1, pos, var == 0 ? UFID : UFID2);
-    }
+    writer.submit(ydata);
     return 0;
   };
   if (write_state()) return 1;
@@ -374,6 +370,7 @@ int run(const Config &c, int rank, int nranks) {
       fflush(stdout);
     }
   }
+  writer.finish();
   if (outproc) cout << "\n   ----------------------\n";
   fclose(UFID);
   fclose(UFID2);
