@@ -324,10 +324,12 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
-template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, bool LC>
+template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, bool LC, int NG>
 __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   constexpr int PITCH = TX + 2;            // points per staged row (west halo + TX + east halo)
   constexpr int RPT = TY * TX / 256;       // rows marched by one thread
+  // NG: row groups the tile arrives in (one mbarrier each)
+  constexpr int GR = (TY + 2 + NG - 1) / NG;
   static_assert(256 % TX == 0 && (TY * TX) % 256 == 0, "tile shape");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2 *tile = reinterpret_cast<double2 *>(smem_raw);                      // [TY+2][PITCH]
@@ -344,21 +346,27 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
 
   if (!LC) {
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    // the staged rows arrive in NG groups, each on its own mbarrier, so the march starts when the first
+    // group has landed instead of waiting for the whole tile
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8u * gi) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const bool west_in = i0 > 0, east_in = i0 + w < nx;           // halo column contiguous with the tile?
     const unsigned row_bytes = (unsigned)(w + (west_in ? 1 : 0) + (east_in ? 1 : 0)) * 16u;
-    const unsigned total = (unsigned)(h + 2) * (unsigned)(w + 2) * 16u;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
     const double2 *y2 = reinterpret_cast<const double2 *>(a.y);
-    for (int r = 0; r < h + 2; ++r) {
-      const long long jr = j0 - 1 + r;
-      const double2 *row = (jr < 0) ? reinterpret_cast<const double2 *>(a.south)
-                         : (jr >= nyl) ? reinterpret_cast<const double2 *>(a.north) : y2 + jr * nx;
-      const unsigned dst = smem_u32(tile + r * PITCH);
-      bulk_g2s(dst + (west_in ? 0u : 16u), row + i0 - (west_in ? 1 : 0), row_bytes, bar);
-      if (!west_in) bulk_g2s(dst, row + (nx - 1), 16u, bar);                    // theta wrap: column nx-1
-      if (!east_in) bulk_g2s(dst + (unsigned)(w + 1) * 16u, row, 16u, bar);     // theta wrap: column 0
+    for (int gi = 0; gi < NG; ++gi) {
+      const int ra = gi * GR, rb = (ra + GR < h + 2) ? ra + GR : h + 2;
+      const unsigned gbytes = (rb > ra) ? (unsigned)(rb - ra) * (unsigned)(w + 2) * 16u : 0u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar + 8u * gi), "r"(gbytes) : "memory");
+      for (int r = ra; r < rb; ++r) {
+        const long long jr = j0 - 1 + r;
+        const double2 *row = (jr < 0) ? reinterpret_cast<const double2 *>(a.south)
+                           : (jr >= nyl) ? reinterpret_cast<const double2 *>(a.north) : y2 + jr * nx;
+        const unsigned dst = smem_u32(tile + r * PITCH);
+        bulk_g2s(dst + (west_in ? 0u : 16u), row + i0 - (west_in ? 1 : 0), row_bytes, bar + 8u * gi);
+        if (!west_in) bulk_g2s(dst, row + (nx - 1), 16u, bar + 8u * gi);                    // theta wrap: column nx-1
+        if (!east_in) bulk_g2s(dst + (unsigned)(w + 1) * 16u, row, 16u, bar + 8u * gi);     // theta wrap: column 0
+      }
     }
   }
   __syncthreads();   // barrier initialised before anyone polls it
@@ -407,21 +415,24 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
     __syncthreads();
   }
 
-  const int c = threadIdx.x % TX;          // column inside the tile
-  const int g0 = (threadIdx.x / TX) * RPT; // first tile row of this thread
+  const int c = (TX == 256) ? threadIdx.x : threadIdx.x % TX;   // column inside the tile
+  const int g0 = (TX == 256) ? 0 : (threadIdx.x / TX) * RPT; // first tile row of this thread (256 threads per CTA)
   double t1 = 0.0, t3 = 0.0;
   const bool active = c < w && g0 < h;
   if (is_torus(MODEL) && active) {
     const double2 tc = reinterpret_cast<const double2 *>(a.cth)[i0 + c];
     t1 = tc.x; t3 = tc.y;
   }
-  // wait for the tile (phase 0)
-  if (!LC) {
+  auto wait_group = [&](int gi) {   // phase 0 of group gi's barrier
     unsigned ok = 0;
     while (!ok) {
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                   : "=r"(ok) : "r"(bar) : "memory");
+                   : "=r"(ok) : "r"(bar + 8u * gi) : "memory");
     }
+  };
+  // rows g0, g0+1, g0+2 of the tile are needed before the first output row
+  if (!LC) {
+    for (int gi = 0; gi <= (g0 + 2) / GR; ++gi) wait_group(gi);
   }
   if (!active) return;
 
@@ -435,6 +446,7 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   double2 *const out0 = out;
   bool bad = (ACC && EXACT && is_torus(MODEL)) ? (a.k.div_safe == 0) : false;
   auto row = [&](int r) {
+    if (!LC && r > 0 && (g0 + r + 2) % GR == 0 && (g0 + r + 2) / GR < NG) wait_group((g0 + r + 2) / GR);   // north row enters a new group
     const double2 nn = col[(r + 1) * PITCH];
     const double uW = col[r * PITCH - 1].x, uE = col[r * PITCH + 1].x;
     double du = !EXACT ? stencil_fast<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x)
@@ -465,13 +477,13 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   }
 }
 
-template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, bool LC>
+template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, bool LC, int NG>
 int launch_tile_lc(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   const long long tiles = ((a.nx + TX - 1) / TX) * ((a.nyl + TY - 1) / TY);
   if (tiles <= 0) return 0;
   if (tiles > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
-  const size_t smem = (size_t)(TY + 2) * (TX + 2) * 16 + 16;
-  auto kern = rhs_tile_kernel<MODEL, EXACT, TX, TY, MINB, ACC, LC>;
+  const size_t smem = (size_t)(TY + 2) * (TX + 2) * 16 + 8 * NG + 8;
+  auto kern = rhs_tile_kernel<MODEL, EXACT, TX, TY, MINB, ACC, LC, NG>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -481,10 +493,10 @@ int launch_tile_lc(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   kern<<<(unsigned)tiles, 256, smem, st>>>(a);
   return check_launch(g->ctx, "rhs_tile_kernel");
 }
-template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC>
+template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, int NG = 3>
 int launch_tile(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
-  return a.nlc > 0 ? launch_tile_lc<MODEL, EXACT, TX, TY, MINB, ACC, true>(g, a, st)
-                   : launch_tile_lc<MODEL, EXACT, TX, TY, MINB, ACC, false>(g, a, st);
+  return a.nlc > 0 ? launch_tile_lc<MODEL, EXACT, TX, TY, MINB, ACC, true, 1>(g, a, st)
+                   : launch_tile_lc<MODEL, EXACT, TX, TY, MINB, ACC, false, NG>(g, a, st);
 }
 
 template <int MODEL, bool EXACT>
@@ -499,7 +511,7 @@ int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
   if (variant == 0) {
     const long long pts = a_in.nx * a_in.nyl;
     if (pts < (4LL << 20)) variant = 1;
-    else variant = (a_in.nx >= 192) ? 13 : (a_in.nx >= 96) ? 10 : 5;
+    else variant = (a_in.nx >= 192) ? ((EXACT && !is_fhn(MODEL)) ? 15 : 13) : (a_in.nx >= 96) ? 10 : 5;   // measured: profiles/README.md
   }
   switch (variant) {
     case 10: return launch_tile<MODEL, EXACT, 128, 16, 4, false>(g, a_in, st);
@@ -508,6 +520,9 @@ int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
     case 13: return launch_tile<MODEL, EXACT, 256, 16, 3, false>(g, a_in, st);
     case 14: return launch_tile<MODEL, EXACT, 128, 16, 3, false>(g, a_in, st);
     case 15: return launch_tile<MODEL, EXACT, 256, 16, 3, true>(g, a_in, st);   // flag-and-redo instead of a branch per point
+    case 16: return launch_tile<MODEL, EXACT, 256, 16, 3, false, 6>(g, a_in, st);  // tile arrives in 6 row groups
+    case 17: return launch_tile<MODEL, EXACT, 256, 16, 3, false, 2>(g, a_in, st);  // ... in 2
+    case 18: return launch_tile<MODEL, EXACT, 256, 16, 3, false, 9>(g, a_in, st);  // ... in 9
     default: break;
   }
   const int RY = (variant == 1) ? 2 : (variant == 2) ? 8 : (variant == 3) ? 1 : 4;

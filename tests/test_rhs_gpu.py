@@ -61,7 +61,7 @@ def test_golden_vectors(crd, ctx, oracle):
 
 
 @pytest.mark.parametrize("model", MODELS)
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 10, 11, 12, 13, 14, 15])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 10, 11, 12, 13, 14, 15, 16, 17])
 def test_parity_vs_oracle(crd, ctx, oracle, model, variant):
     for (nx, ny) in ((400, 1600) if variant in (0, 10) else (100, 400), (3, 2), (2, 3), (257, 31), (31, 257), (128, 16), (129, 17)):
         for t in (10.0, 50.0):
