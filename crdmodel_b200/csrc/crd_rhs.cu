@@ -372,8 +372,8 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   __syncthreads();   // barrier initialised before anyone polls it
   } else {
     // fused stage assembly: the tile is the combination sum_j c_j x_j, formed while it is staged (the stage
-    // state is never written to HBM).  Plain coalesced 16-byte loads; each thread stages its own column, four
-    // rows per pass so that 4 loads per input vector are in flight, then the few halo-column entries.
+    // state is never written to HBM).  Plain coalesced 16-byte loads; each thread stages its own column, nine
+    // rows per pass (9 loads per input vector in flight per thread), then the few halo-column entries.
     auto generic = [&](int r, int sc) {
       const long long jr = j0 - 1 + r;
       const long long col = (sc == 0) ? (i0 == 0 ? nx - 1 : i0 - 1) : (sc == w + 1) ? (i0 + w == nx ? 0 : i0 + w) : i0 + sc - 1;
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
       tile[r * PITCH + sc] = v;
     };
     const int r_lo = (j0 == 0) ? 1 : 0, r_hi = (j0 + h == nyl) ? h + 1 : h + 2;   // tile rows that are rows of this launch
-    constexpr int R = 4;
+    constexpr int R = 9;   // (TY + 2) = 18 rows in two passes, 9 loads per input vector in flight per thread
     for (int tcol = threadIdx.x; tcol < w; tcol += 256) {
       const long long p0 = (j0 - 1) * nx + i0 + tcol;   // point offset of tile row 0 in this column
       for (int rb = r_lo; rb < r_hi; rb += R) {
@@ -499,6 +499,192 @@ int launch_tile(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
                    : launch_tile_lc<MODEL, EXACT, TX, TY, MINB, ACC, false, NG>(g, a, st);
 }
 
+// ---- the streaming kernel: persistent CTAs, rows flow through a shared-memory ring ------------------------
+// 2 CTAs per SM stay resident and walk over (strip of 256 columns) x (segment of rows) units.  Warp 8 is the
+// producer: one lane issues a 1-D TMA bulk copy per row and input vector into the next free ring slot and arms
+// that slot's "full" mbarrier with the byte count.  Warps 0..7 are consumers: a thread owns one column, waits for
+// the slot, reads (and, for a fused stage, combines sum_j c_j x_j of) its point and the two neighbours' u, releases
+// the slot on the "empty" mbarrier, and with the previous two rows still in registers computes the row before.
+// Every state row is fetched once (plus one halo row per segment end); no CTA start-up per tile.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok = 0;
+  while (!ok) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+
+template <int MODEL, bool EXACT, int NV, bool PLAIN, int RB>
+__global__ void __launch_bounds__(288, 2) rhs_stream_kernel(const RhsArgs a, int seg_rows, int S) {
+  constexpr int TX = 256, PITCH = TX + 2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double2 *ring = reinterpret_cast<double2 *>(smem_raw);                       // [S][RB][NV][PITCH]
+  const unsigned bars = smem_u32(smem_raw + (size_t)S * RB * NV * PITCH * 16); // full[S], empty[S]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long nx = a.nx, nyl = a.nyl;
+  const long long strips = (nx + TX - 1) / TX, segs = (nyl + seg_rows - 1) / seg_rows, units = strips * segs;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * s) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(bars + 8u * (S + s)) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 8) {   // ---------------- producer ----------------
+    if (lane != 0) return;
+    long long it = 0;   // stage counter
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const long long strip = u % strips, seg = u / strips;
+      const long long i0 = strip * TX, jA = seg * seg_rows, jB = (jA + seg_rows < nyl) ? jA + seg_rows : nyl;
+      const int w = (nx - i0 < TX) ? (int)(nx - i0) : TX;
+      const bool west_in = i0 > 0, east_in = i0 + w < nx;
+      const unsigned row_bytes = (unsigned)(w + (west_in ? 1 : 0) + (east_in ? 1 : 0)) * 16u;
+      for (long long j0 = jA - 1; j0 <= jB; j0 += RB, ++it) {   // a stage = rows j0 .. j0+RB-1 (clipped at jB)
+        const int s = (int)(it % S);
+        mbar_wait(bars + 8u * (S + s), (unsigned)((it / S) & 1) ^ 1u);
+        const int nr = (jB - j0 + 1 < RB) ? (int)(jB - j0 + 1) : RB;
+        unsigned bytes = 0;
+        for (int rr = 0; rr < nr; ++rr) {
+          const long long jr = j0 + rr;
+          const bool ext = (jr < 0 && a.south) || (jr >= nyl && a.north);
+          bytes += (unsigned)((PLAIN || ext) ? 1 : NV) * (unsigned)(w + 2) * 16u;
+        }
+        const unsigned full = bars + 8u * s;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
+        for (int rr = 0; rr < nr; ++rr) {
+          const long long jr = j0 + rr;
+          const bool ext = (jr < 0 && a.south) || (jr >= nyl && a.north);   // an already combined ghost row
+          const int nvec = (PLAIN || ext) ? 1 : NV;
+          for (int v = 0; v < nvec; ++v) {
+            const double2 *row;
+            if (ext) row = reinterpret_cast<const double2 *>(jr < 0 ? a.south : a.north);
+            else if (PLAIN) row = reinterpret_cast<const double2 *>(a.y) + jr * nx;
+            else {
+              const long long off = (jr < 0) ? a.south_off : (jr >= nyl) ? a.north_off : jr * nx;
+              row = reinterpret_cast<const double2 *>(a.lc_x[v]) + off;
+            }
+            const unsigned dst = smem_u32(ring + (((size_t)s * RB + rr) * NV + v) * PITCH);
+            bulk_g2s(dst + (west_in ? 0u : 16u), row + i0 - (west_in ? 1 : 0), row_bytes, full);
+            if (!west_in) bulk_g2s(dst, row + (nx - 1), 16u, full);
+            if (!east_in) bulk_g2s(dst + (unsigned)(w + 1) * 16u, row, 16u, full);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const int c = threadIdx.x;   // 0..255: column inside the strip
+  const int react_on = a.react;
+  long long it = 0;
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    const long long strip = u % strips, seg = u / strips;
+    const long long i0 = strip * TX, jA = seg * seg_rows, jB = (jA + seg_rows < nyl) ? jA + seg_rows : nyl;
+    const int w = (nx - i0 < TX) ? (int)(nx - i0) : TX;
+    const bool active = c < w;
+    double t1 = 0.0, t3 = 0.0;
+    if (is_torus(MODEL) && active) {
+      const double2 tc = reinterpret_cast<const double2 *>(a.cth)[i0 + c];
+      t1 = tc.x; t3 = tc.y;
+    }
+    double2 *out = reinterpret_cast<double2 *>(a.ydot) + jA * nx + (i0 + c);
+    double uS = 0.0, cW = 0.0, cE = 0.0;
+    double2 cc = make_double2(0.0, 0.0);
+    // one row: fetch (and combine) the arriving row jr, then emit row jr-1 from the three rows in registers
+    auto step = [&](const double2 *slot, long long jr) {
+      const bool ext = (jr < 0 && a.south) || (jr >= nyl && a.north);
+      double2 nn;
+      double nW, nE;
+      if (PLAIN || ext) {
+        nn = slot[c + 1]; nW = slot[c].x; nE = slot[c + 2].x;
+      } else {
+        double2 v[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = slot[j * PITCH + c + 1];
+        nn = make_double2(a.lc_c[0] * v[0].x, a.lc_c[0] * v[0].y);
+#pragma unroll
+        for (int j = 1; j < NV; ++j) { nn.x = fma(a.lc_c[j], v[j].x, nn.x); nn.y = fma(a.lc_c[j], v[j].y, nn.y); }
+        nW = __shfl_up_sync(0xffffffffu, nn.x, 1);
+        nE = __shfl_down_sync(0xffffffffu, nn.x, 1);
+        if (lane == 0 || lane == 31) {   // the neighbour lives in another warp: combine its u from the slot
+          const int q = (lane == 0) ? c : c + 2;
+          double e = a.lc_c[0] * slot[q].x;
+#pragma unroll
+          for (int j = 1; j < NV; ++j) e = fma(a.lc_c[j], slot[j * PITCH + q].x, e);
+          if (lane == 0) nW = e; else nE = e;
+        }
+      }
+      if (jr > jA) {   // rows jr-2 (uS), jr-1 (cc) and jr (nn) are here: output row jr-1
+        const long long jl = jr - 1;
+        double du = EXACT ? stencil_exact<MODEL>(a.k, t1, t3, cc.x, cW, cE, uS, nn.x)
+                          : stencil_fast<MODEL>(a.k, t1, t3, cc.x, cW, cE, uS, nn.x);
+        double dv = 0.0;
+        if (react_on) {
+          react<MODEL, EXACT>(a.k, __ldg(a.brow + jl), cc.x, cc.y, du, dv);
+          const bool frozen = (a.freeze_north && jl == nyl - 1) || (a.freeze_south && jl == 0);
+          du = frozen ? 0.0 : du;
+          dv = frozen ? 0.0 : dv;
+        }
+        if (active) *out = make_double2(du, dv);
+        out += nx;
+      }
+      uS = cc.x; cc = nn; cW = nW; cE = nE;
+    };
+    for (long long j0 = jA - 1; j0 <= jB; j0 += RB, ++it) {
+      const int s = (int)(it % S);
+      mbar_wait(bars + 8u * s, (unsigned)((it / S) & 1));
+      const double2 *stage = ring + (size_t)s * RB * NV * PITCH;
+      const int nr = (jB - j0 + 1 < RB) ? (int)(jB - j0 + 1) : RB;
+      if (nr == RB) {
+#pragma unroll
+        for (int rr = 0; rr < RB; ++rr) step(stage + (size_t)rr * NV * PITCH, j0 + rr);
+      } else {
+        for (int rr = 0; rr < nr; ++rr) step(stage + (size_t)rr * NV * PITCH, j0 + rr);
+      }
+      __syncwarp();   // every lane has read the stage (the values it still needs are in registers)
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8u * (S + s)) : "memory");
+    }
+  }
+}
+
+template <int MODEL, bool EXACT, int NV, bool PLAIN>
+int launch_stream_nv(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+  constexpr int RB = (NV == 1) ? 4 : (NV <= 3 ? 2 : 1);   // rows per ring stage
+  const int seg_rows = 128;
+  const long long strips = (a.nx + 255) / 256, segs = (a.nyl + seg_rows - 1) / seg_rows, units = strips * segs;
+  if (units <= 0) return 0;
+  const size_t stage_bytes = (size_t)RB * NV * 258 * 16;
+  int S = (int)(100000 / stage_bytes);
+  if (S > 8) S = 8;
+  if (S < 3) S = 3;
+  const size_t smem = (size_t)S * stage_bytes + (size_t)2 * S * 8;
+  auto kern = rhs_stream_kernel<MODEL, EXACT, NV, PLAIN, RB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110000);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+    attr_set = true;
+  }
+  const long long ctas = units < 2LL * kSMs ? units : 2LL * kSMs;
+  kern<<<(unsigned)ctas, 288, smem, st>>>(a, seg_rows, S);
+  return check_launch(g->ctx, "rhs_stream_kernel");
+}
+
+template <int MODEL, bool EXACT>
+int launch_stream(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+  switch (a.nlc) {
+    case 0: return launch_stream_nv<MODEL, EXACT, 1, true>(g, a, st);
+    case 2: return launch_stream_nv<MODEL, EXACT, 2, false>(g, a, st);
+    case 3: return launch_stream_nv<MODEL, EXACT, 3, false>(g, a, st);
+    case 5: return launch_stream_nv<MODEL, EXACT, 5, false>(g, a, st);
+    default: return 1;   // other counts: caller falls back to the tiled kernel
+  }
+}
+
 template <int MODEL, bool EXACT>
 int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
   // variant 0 = automatic.  Large slabs (>= 4 Mi points, HBM-bound): the TMA-tiled kernel wherever a tile row is
@@ -512,6 +698,14 @@ int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
     const long long pts = a_in.nx * a_in.nyl;
     if (pts < (4LL << 20)) variant = 1;
     else variant = (a_in.nx >= 192) ? ((EXACT && !is_fhn(MODEL)) ? 15 : 13) : (a_in.nx >= 96) ? 10 : 5;   // measured: profiles/README.md
+  }
+  // measured (profiles/README.md): the streaming kernel wins only for the widest fused stage (5 input vectors,
+  // where its once-per-row fetch beats the tiled kernel's register-staged tiles); the tiled kernel everywhere else
+  if (g->variant == 0 && a_in.nlc == 5 && a_in.nx >= 192 && a_in.nx * a_in.nyl >= (4LL << 20)) variant = 20;
+  if (variant == 20) {   // streaming kernel (persistent CTAs, shared-memory row ring)
+    const int r = launch_stream<MODEL, EXACT>(g, a_in, st);
+    if (r <= 0) return r;
+    variant = 13;
   }
   switch (variant) {
     case 10: return launch_tile<MODEL, EXACT, 128, 16, 4, false>(g, a_in, st);

@@ -61,7 +61,7 @@ def test_golden_vectors(crd, ctx, oracle):
 
 
 @pytest.mark.parametrize("model", MODELS)
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 10, 11, 12, 13, 14, 15, 16, 17])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 10, 11, 12, 13, 14, 15, 16, 17, 20])
 def test_parity_vs_oracle(crd, ctx, oracle, model, variant):
     for (nx, ny) in ((400, 1600) if variant in (0, 10) else (100, 400), (3, 2), (2, 3), (257, 31), (31, 257), (128, 16), (129, 17)):
         for t in (10.0, 50.0):
@@ -207,7 +207,7 @@ def test_exact_division_edge_values(crd, ctx, oracle):
                 yy = np.abs(yy)
             P = oracle.make_params(model, nx, ny, just_diffusion=1 if model == "gb_torus" else 0)
             ref = oracle.rhs(P, 50.0, yy)
-            for variant in (0, 10):
+            for variant in (0, 10, 20):
                 got = gpu_rhs(crd, ctx, model, nx, ny, 50.0, yy, crd.ARITH_EXACT, variant, just_diffusion=1 if model == "gb_torus" else 0)
                 assert got.tobytes() == ref.tobytes(), (model, k, variant)
 
@@ -221,7 +221,7 @@ def test_fused_stage_rhs_equals_lincomb_then_rhs(crd, ctx, oracle, model):
         n_el = 2 * nx * ny
         X = [oracle.fill_state(model, n_el, seed=40 + j) for j in range(5)]
         for ncomb, coefs in ((1, [1.0]), (2, [1.0, 0.013]), (3, [1.0, 0.02, -0.007]), (5, [1.0, 0.004, 0.005, 0.009, -0.001])):
-            for variant in (0, 1, 5, 10, 13):
+            for variant in (0, 1, 5, 10, 13, 20):
                 g = crd.Grid(ctx, crd.make_params(model, nx, ny, t_boundary=38.0))
                 g.set_variant(variant)
                 V = [crd.NVector.from_numpy(ctx, x) for x in X[:ncomb]]
