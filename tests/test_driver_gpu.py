@@ -151,3 +151,40 @@ def test_shipped_fhn_ini_keys_are_accepted(crd, tmp_path):
     assert "nx = 16" in out and "ny = 64" in out
     u = np.loadtxt(tmp_path / "flat" / "FHNmodel_flat_u.000.txt")
     assert u.shape == (5, 16 * 64) and np.isfinite(u).all()
+
+
+FLAT_GB_INI = GB_INI.replace("waveInside = 1\n", "").replace("icType = 0", "icType = 1").replace("varyBeta = 0", "varyBeta = {vb}")
+
+
+@pytest.mark.parametrize("exe,model,ini", [
+    ("FHNmodel_flat", "fhn_flat", FHN_INI.format(vb=0, inside=0)),
+    ("GoldbeterModel_flat", "gb_flat", FLAT_GB_INI.format(vb=0)),
+    ("GoldbeterModel_flat", "gb_flat", FLAT_GB_INI.format(vb=1)),
+])
+def test_flat_drivers_match_reference_main(crd, oracle, tmp_path, exe, model, ini):
+    if not oracle.ref_available(model):
+        pytest.skip("oracle/_ref not built")
+    from crdmodel_b200 import build as B
+    B.build_drivers()
+    bindir = tmp_path / "path"
+    bindir.mkdir()
+    script = bindir / "SolveGoldbeterODE.py"
+    script.write_text("#!/bin/sh\necho '[0.392] [1.6469]'\n")
+    script.chmod(0o755)
+    os.environ["PATH"] = str(bindir) + os.pathsep + os.environ["PATH"]
+    out_gpu = run_driver(exe, ini, str(tmp_path / "gpu"))
+    out_cpu = run_reference(oracle, model, ini, str(tmp_path / "cpu"))
+    head = lambda s: s[:s.index("rtol")]
+    assert head(out_gpu) == head(out_cpu)
+    g, c = tmp_path / "gpu", tmp_path / "cpu"
+    names = sorted(p.name for p in g.iterdir() if p.name.endswith(".txt"))
+    assert names == sorted(p.name for p in c.iterdir() if p.name.endswith(".txt")) and len(names) == 3
+    for n in names:
+        a, b = (g / n).read_text().splitlines(), (c / n).read_text().splitlines()
+        assert len(a) == len(b)
+        if "subdomain" in n:
+            assert a == b
+            continue
+        assert a[0] == b[0]
+        A, Bm = np.array([l.split() for l in a], float), np.array([l.split() for l in b], float)
+        assert A.shape == Bm.shape and np.all(np.abs(A - Bm) <= 20 * (1e-5 * np.abs(Bm) + 1e-10))

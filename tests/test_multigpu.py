@@ -19,3 +19,51 @@ def test_ring_across_gpus(crd, oracle):
                         "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "mgpu_worker.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_driver_on_two_gpus_matches_one_gpu(crd, tmp_path):
+    """bin/FHNmodel_torus with System.gpus = 2 (forked workers, IPC halo ring, shared-memory allreduce): the two
+    subdomain file sets, stacked by their js/je, equal the single-GPU output within the integrator tolerance."""
+    import numpy as np
+    if crd.lib().crd_device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from crdmodel_b200 import build as B
+    B.build_drivers()
+    ini = """[Parameters]
+diffusion = 0.12
+beta = 1.25
+surfaceWidth = 20
+surfaceLength = 80
+waveLength = 0.1
+waveWidth = 0.5
+waveInside = 1
+outputTimestep = 3
+tBoundary = 0.5
+tFinal = 1.5
+thetaMesh = 40
+betaMin = 0.7
+betaMax = 1.7
+
+[System]
+includeAllVars = 1
+varyBeta = 0
+gpus = %d
+"""
+    outs = {}
+    for ng in (1, 2):
+        d = tmp_path / ("g%d" % ng)
+        d.mkdir()
+        (d / "a.ini").write_text(ini % ng)
+        r = subprocess.run([os.path.join(ROOT, "bin", "FHNmodel_torus"), str(d / "a.ini")], cwd=str(d), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert ("nprocs = %d" % ng) in r.stdout
+        rows = []
+        for rk in range(ng):
+            sub = (d / ("FHNmodel_torus_subdomain.%03d.txt" % rk)).read_text().split()
+            nx, ny, js, je = int(sub[0]), int(sub[1]), int(sub[4]), int(sub[5])
+            u = np.loadtxt(d / ("FHNmodel_torus_u.%03d.txt" % rk)).reshape(4, je - js + 1, nx)
+            rows.append((js, u))
+        outs[ng] = np.concatenate([u for _, u in sorted(rows, key=lambda t: t[0])], axis=1)
+        assert outs[ng].shape == (4, 160, 40)
+    assert np.array_equal(outs[1][0], outs[2][0])
+    assert np.all(np.abs(outs[1] - outs[2]) <= 20 * (1e-5 * np.abs(outs[1]) + 1e-10))
