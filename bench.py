@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg5"],
                     help="cfg4: FHN torus 16384 x 16384 per GPU (BASELINE configs[3], the headline); "
                          "cfg5: Goldbeter torus theta 8192 x 4096 phi rows per GPU (configs[4], global 8192 x 32768 at 8 GPUs)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: keep the GLOBAL mesh of the workload (cfg4: 16384 x 16384) and give each GPU 1/N of its rows")
     ap.add_argument("--rows-per-gpu", type=int, default=None)
     ap.add_argument("--nx", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -219,6 +221,8 @@ def main():
     model = "fhn_torus" if args.workload == "cfg4" else "gb_torus"
     nx = args.nx or (NX if args.workload == "cfg4" else 8192)
     nyl = args.rows_per_gpu or (ROWS_PER_GPU if args.workload == "cfg4" else 4096)
+    if args.strong:
+        nyl = (ROWS_PER_GPU if args.workload == "cfg4" else 32768) // world
     ny = nyl * world
     js, je = crd.decomp_phi(ny, world, rank)
     arith = crd.ARITH_EXACT if args.arith == "exact" else crd.ARITH_FAST
@@ -326,7 +330,7 @@ def main():
                 traffic = None
         metric = METRIC if model == "fhn_torus" else "Goldbeter-torus grid-point RHS evals/sec (fp64)"
         line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": "BASELINE configs[%d]: %s torus RHS f(t,y), synthetic LCG state, theta %d x phi %d per GPU "
                                        "(global phi %d), phi-split ring of %d GPU(s)" % (3 if model == "fhn_torus" else 4,

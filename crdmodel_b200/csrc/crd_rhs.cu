@@ -34,22 +34,8 @@ __host__ __device__ constexpr bool is_fhn(int model) { return model == CRD_FHN_T
 // q0 = RN(a*rc) is within 1.5 ulp of a/c; one residual step makes it faithful, and by Markstein's
 // theorem (q faithful, rc = RN(1/c), r = a - c*q exact through FMA  =>  RN(q + r*rc) = RN(a/c)) the
 // second step is the correctly rounded quotient: 5 FP64 issues instead of the ~20 of a general
-// division.  Outside the safely normal range (zero, tiny, huge, inf/nan) it falls back to the IEEE
-// division so signed zeros and subnormals also match.
-__device__ __forceinline__ double div_const_rn(double a, double c, double rc) {
-  double q = __dmul_rn(a, rc);
-  // biased exponent of q in [123, 1923)  <=>  2^-900 <= |q| < 2^900 (integer test: keeps the FP64 pipe free)
-  const unsigned eq = ((unsigned)__double2hiint(q) >> 20) & 0x7ffu;
-  if (eq - 123u < 1800u) {
-    double r = __fma_rn(-q, c, a);
-    q = __fma_rn(r, rc, q);
-    r = __fma_rn(-q, c, a);
-    return __fma_rn(r, rc, q);
-  }
-  if (a == 0.0) return q;  // (+-0)*rc carries the sign of a/c; uniform regions of the field take this exit
-  return __ddiv_rn(a, c);
-}
-
+// division.  Outside the safely normal range (tiny, huge, inf/nan) the caller falls back to the IEEE
+// division so subnormals also match.
 // Straight-line form used by the stencil (so the three divisions of a point and the points of a thread
 // interleave and hide the FP64 latency).  Needs c > 0.  The residual is formed as r' = q*c - a and
 // subtracted, which makes a zero numerator come out as the correctly signed zero with no special case:
@@ -194,28 +180,34 @@ __device__ __forceinline__ void react(const RhsConst &k, double b, double u, dou
 // ---- state access: plain vector, or sum_j c_j x_j formed on the fly (same operation order as lincomb_kernel) ---
 template <bool LC>
 __device__ __forceinline__ double2 state2(const RhsArgs &a, long long p) {
-  if (!LC) return reinterpret_cast<const double2 *>(a.y)[p];
-  double2 v[kMaxLc];
+  if constexpr (!LC) {
+    return reinterpret_cast<const double2 *>(a.y)[p];
+  } else {
+    double2 v[kMaxLc];
 #pragma unroll
-  for (int j = 0; j < kMaxLc; ++j)
-    v[j] = (j < a.nlc) ? reinterpret_cast<const double2 *>(a.lc_x[j])[p] : make_double2(0.0, 0.0);
-  double2 s = make_double2(a.lc_c[0] * v[0].x, a.lc_c[0] * v[0].y);
+    for (int j = 0; j < kMaxLc; ++j)
+      v[j] = (j < a.nlc) ? reinterpret_cast<const double2 *>(a.lc_x[j])[p] : make_double2(0.0, 0.0);
+    double2 s = make_double2(a.lc_c[0] * v[0].x, a.lc_c[0] * v[0].y);
 #pragma unroll
-  for (int j = 1; j < kMaxLc; ++j)
-    if (j < a.nlc) { s.x = fma(a.lc_c[j], v[j].x, s.x); s.y = fma(a.lc_c[j], v[j].y, s.y); }
-  return s;
+    for (int j = 1; j < kMaxLc; ++j)
+      if (j < a.nlc) { s.x = fma(a.lc_c[j], v[j].x, s.x); s.y = fma(a.lc_c[j], v[j].y, s.y); }
+    return s;
+  }
 }
 template <bool LC>
 __device__ __forceinline__ double stateu(const RhsArgs &a, long long p) {
-  if (!LC) return a.y[2 * p];
-  double v[kMaxLc];
+  if constexpr (!LC) {
+    return a.y[2 * p];
+  } else {
+    double v[kMaxLc];
 #pragma unroll
-  for (int j = 0; j < kMaxLc; ++j) v[j] = (j < a.nlc) ? a.lc_x[j][2 * p] : 0.0;
-  double s = a.lc_c[0] * v[0];
+    for (int j = 0; j < kMaxLc; ++j) v[j] = (j < a.nlc) ? a.lc_x[j][2 * p] : 0.0;
+    double s = a.lc_c[0] * v[0];
 #pragma unroll
-  for (int j = 1; j < kMaxLc; ++j)
-    if (j < a.nlc) s = fma(a.lc_c[j], v[j], s);
-  return s;
+    for (int j = 1; j < kMaxLc; ++j)
+      if (j < a.nlc) s = fma(a.lc_c[j], v[j], s);
+    return s;
+  }
 }
 // u of the row below / above the launch's rows at column i
 template <bool LC>
