@@ -197,6 +197,18 @@ def main():
     import crdmodel_b200 as crd
     from crdmodel_b200 import dist as cdist
 
+    # host buffers of the e2e leg should live on the GPU's own NUMA node: bind this rank's thread to the GPU-local
+    # cores before anything is allocated (restored before the CPU baseline, which uses every core)
+    all_cpus = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [int(x) for x in vis.split(",")] if vis and all(x.strip().isdigit() for x in vis.split(",")) else []
+        phys = ids[local_rank] if local_rank < len(ids) else local_rank
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+    except Exception:
+        pass
     torch.cuda.set_device(local_rank)
     use_dist = world > 1
     gloo = None
@@ -349,6 +361,7 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "integrator": integ}
         if world == 1 and not args.no_cpu_baseline:
             try:
+                os.sched_setaffinity(0, all_cpus)
                 line["cpu_baseline"] = cpu_baseline(model, nx)
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % str(e)[:120]}
