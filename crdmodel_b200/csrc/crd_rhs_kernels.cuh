@@ -1,0 +1,873 @@
+// crd_rhs_kernels.cuh — device code of the right-hand side: per-point arithmetic (EXACT / FAST), the direct,
+// tiled (TMA bulk-copy) and streaming (persistent, mbarrier row ring) kernels, the halo push / wait kernels, the
+// initial-condition kernel, and their launchers.  Included once, by crd_rhs.cu, which holds the C ABI.
+#pragma once
+#include <cmath>
+#include <vector>
+
+#include "crd_grid.cuh"
+
+using namespace crd;
+
+namespace {
+
+constexpr double kEps = 0.36;   // EPSILON, FHNmodel_torus.cpp:68
+constexpr double kPI = 3.1415926535897932;  // FHNmodel_torus.cpp:63
+// Goldbeter constants, GoldbeterModel_torus.cpp:67-78
+constexpr double G_v0 = 1.0, G_k = 10.0, G_kf = 1.0, G_v1 = 7.3, G_VM2 = 65.0, G_VM3 = 500.0;
+constexpr double G_K2 = 1.0, G_KR = 2.0, G_KA = 0.9, G_m = 2.0, G_n = 2.0, G_p = 4.0;
+
+__host__ __device__ constexpr bool is_torus(int model) { return model == CRD_FHN_TORUS || model == CRD_GOLDBETER_TORUS; }
+__host__ __device__ constexpr bool is_fhn(int model) { return model == CRD_FHN_TORUS || model == CRD_FHN_FLAT; }
+
+// ---- per-point arithmetic ---------------------------------------------------------------------------
+// Correctly rounded a / c for a divisor known in advance, rc = RN(1/c) from the host's IEEE division.
+// q0 = RN(a*rc) is within 1.5 ulp of a/c; one residual step makes it faithful, and by Markstein's
+// theorem (q faithful, rc = RN(1/c), r = a - c*q exact through FMA  =>  RN(q + r*rc) = RN(a/c)) the
+// second step is the correctly rounded quotient: 5 FP64 issues instead of the ~20 of a general
+// division.  Outside the safely normal range (tiny, huge, inf/nan) the caller falls back to the IEEE
+// division so subnormals also match.
+// Straight-line form used by the stencil (so the three divisions of a point and the points of a thread
+// interleave and hide the FP64 latency).  Needs c > 0.  The residual is formed as r' = q*c - a and
+// subtracted, which makes a zero numerator come out as the correctly signed zero with no special case:
+//   a = -0: q0 = -0, r' = fma(-0, c, +0) = +0, q = fma(-(+0), rc, -0) = -0;   a = +0: likewise +0.
+__device__ __forceinline__ double div_const_line(double a, double c, double rc) {
+  const double q0 = __dmul_rn(a, rc);
+  double r = __fma_rn(q0, c, -a);
+  const double q1 = __fma_rn(-r, rc, q0);
+  r = __fma_rn(q1, c, -a);
+  return __fma_rn(-r, rc, q1);
+}
+// true when the numerator is outside the range where div_const_line is proven (|n| in [2^-800, 2^800),
+// divisor within 2^+-90, checked on the host) and is not an exact zero; integer tests only
+__device__ __forceinline__ bool div_needs_ieee(double n) {
+  const unsigned hi = (unsigned)__double2hiint(n) & 0x7fffffffu;
+  const bool inrange = (hi - 0x0DF00000u) < 0x64000000u;   // biased exponent in [223, 1823)
+  return !inrange && (hi | (unsigned)__double2loint(n)) != 0u;
+}
+
+// 1/x to ~1 ulp without the IEEE slow path (FAST arithmetic only; x is a sum of positive terms here)
+__device__ __forceinline__ double rcp_fast(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+// the same sum with IEEE divisions; kept out of line so the unrolled hot loop does not carry 3 divisions per row
+__device__ __noinline__ double stencil_sum_ieee(double n1, double n2, double n3, double c1, double c2, double c3) {
+  return __dadd_rn(__dadd_rn(__ddiv_rn(n1, c1), __ddiv_rn(n2, c2)), __ddiv_rn(n3, c3));
+}
+
+// all three numerators at once: min / max of the high words decide the common case in 8 integer instructions
+__device__ __forceinline__ bool div3_needs_ieee(double n1, double n2, double n3) {
+  const unsigned t1 = (unsigned)__double2hiint(n1) & 0x7fffffffu, t2 = (unsigned)__double2hiint(n2) & 0x7fffffffu,
+                 t3 = (unsigned)__double2hiint(n3) & 0x7fffffffu;
+  const unsigned mn = min(t1, min(t2, t3)), mx = max(t1, max(t2, t3));
+  if (mn >= 0x0DF00000u && mx < 0x71F00000u) return false;        // every |n| in [2^-800, 2^800)
+  return div_needs_ieee(n1) || div_needs_ieee(n2) || div_needs_ieee(n3);   // zeros are fine, the rest is not
+}
+
+// EXACT: the reference's expression tree with separately rounded operations.
+template <int MODEL>
+__device__ __forceinline__ double stencil_exact(const RhsConst &k, double a1, double a3, double uC, double uW,
+                                                double uE, double uS, double uN) {
+  if (is_torus(MODEL)) {
+    // :535-537   Diff*(a1*(uE-uW))/(2dx) + Diff*((1/r^2)*(uE-2uC+uW))/(dx*dx) + Diff*(a3*(uN-2uC+uS))/(dy*dy)
+    const double two_uC = __dmul_rn(2.0, uC);
+    const double n1 = __dmul_rn(k.Diff, __dmul_rn(a1, __dsub_rn(uE, uW)));
+    const double n2 = __dmul_rn(k.Diff, __dmul_rn(k.inv_rr, __dadd_rn(__dsub_rn(uE, two_uC), uW)));
+    const double n3 = __dmul_rn(k.Diff, __dmul_rn(a3, __dadd_rn(__dsub_rn(uN, two_uC), uS)));
+    double T1 = div_const_line(n1, k.twodx, k.r_twodx);
+    double T2 = div_const_line(n2, k.dxdx, k.r_dxdx);
+    double T3 = div_const_line(n3, k.dydy, k.r_dydy);
+    if (!k.div_safe || div3_needs_ieee(n1, n2, n3))
+      return stencil_sum_ieee(n1, n2, n3, k.twodx, k.dxdx, k.dydy);  // tiny / huge / non-finite numerator: rare, out of line
+    return __dadd_rn(__dadd_rn(T1, T2), T3);
+  } else {
+    // FHNmodel_flat.cpp:496-498   cu1*(uW+uE) + cu2*(uS+uN) + cu3*uC
+    return __dadd_rn(__dadd_rn(__dmul_rn(k.cu1, __dadd_rn(uW, uE)), __dmul_rn(k.cu2, __dadd_rn(uS, uN))),
+                     __dmul_rn(k.cu3, uC));
+  }
+}
+
+// Same sum, but instead of branching per point it ORs "this point needs the IEEE path" into `bad`; the caller
+// redoes the flagged thread's rows afterwards.  Keeps the marched rows free of control flow so they interleave.
+template <int MODEL>
+__device__ __forceinline__ double stencil_exact_acc(const RhsConst &k, double a1, double a3, double uC, double uW,
+                                                    double uE, double uS, double uN, bool &bad) {
+  if (is_torus(MODEL)) {
+    const double two_uC = __dmul_rn(2.0, uC);
+    const double n1 = __dmul_rn(k.Diff, __dmul_rn(a1, __dsub_rn(uE, uW)));
+    const double n2 = __dmul_rn(k.Diff, __dmul_rn(k.inv_rr, __dadd_rn(__dsub_rn(uE, two_uC), uW)));
+    const double n3 = __dmul_rn(k.Diff, __dmul_rn(a3, __dadd_rn(__dsub_rn(uN, two_uC), uS)));
+    bad = bad | div_needs_ieee(n1) | div_needs_ieee(n2) | div_needs_ieee(n3);
+    return __dadd_rn(__dadd_rn(div_const_line(n1, k.twodx, k.r_twodx), div_const_line(n2, k.dxdx, k.r_dxdx)),
+                     div_const_line(n3, k.dydy, k.r_dydy));
+  } else {
+    return stencil_exact<MODEL>(k, a1, a3, uC, uW, uE, uS, uN);
+  }
+}
+
+template <int MODEL>
+__device__ __forceinline__ double stencil_fast(const RhsConst &k, double c1, double c3, double uC, double uW,
+                                               double uE, double uS, double uN) {
+  if (is_torus(MODEL)) {
+    const double m2 = -2.0 * uC;
+    return c1 * (uE - uW) + k.c2 * ((uE + m2) + uW) + c3 * ((uN + m2) + uS);
+  } else {
+    return k.cu1 * (uW + uE) + k.cu2 * (uS + uN) + k.cu3 * uC;
+  }
+}
+
+// x^4 rounded once (libm's pow(x, 4.0) is correctly rounded for nearly every argument, (x*x)*(x*x) is not)
+__device__ __forceinline__ double pow4_rn(double x, double x2) {
+  const double e2 = __fma_rn(x, x, -x2);          // x*x = x2 + e2 exactly
+  const double p = __dmul_rn(x2, x2);
+  const double pe = __fma_rn(x2, x2, -p);         // x2*x2 = p + pe exactly
+  return __dadd_rn(p, __fma_rn(__dmul_rn(2.0, x2), e2, pe));
+}
+
+template <int MODEL, bool EXACT>
+__device__ __forceinline__ void react(const RhsConst &k, double b, double u, double v, double &du, double &dv) {
+  if (is_fhn(MODEL)) {
+    if (EXACT) {
+      // :657  ydot_u += 3u - u*u*u - v      :660  ydot_v += EPSILON*(u + b)
+      du = __dadd_rn(du, __dsub_rn(__dsub_rn(__dmul_rn(3.0, u), __dmul_rn(__dmul_rn(u, u), u)), v));
+      // ydot_v starts at 0.0 (N_VConst :506): 0.0 + x differs from x only for x = -0, i.e. u = b = -0
+      dv = __dmul_rn(kEps, __dadd_rn(u, b));
+      if (k.dv_plus0) dv = __dadd_rn(0.0, dv);
+    } else {
+      du += (3.0 * u - u * u * u) - v;
+      dv = kEps * (u + b);
+    }
+  } else {
+    // GoldbeterModel_torus.cpp:694-695,715-716; b carries v0 + v1*beta(phi)
+    const double Z = u, Y = v;
+    if (EXACT) {
+      const double z2 = __dmul_rn(Z, Z), y2 = __dmul_rn(Y, Y);
+      const double z4 = pow4_rn(Z, z2);
+      const double v2 = __ddiv_rn(__dmul_rn(G_VM2, z2), __dadd_rn(k.k2n, z2));
+      const double v3 = __ddiv_rn(__dmul_rn(__dmul_rn(G_VM3, y2), z4),
+                                  __dmul_rn(__dadd_rn(k.krm, y2), __dadd_rn(k.kap, z4)));
+      du = __dadd_rn(du, __dsub_rn(__dadd_rn(__dadd_rn(__dsub_rn(b, v2), v3), __dmul_rn(G_kf, Y)), __dmul_rn(G_k, Z)));
+      dv = __dsub_rn(__dsub_rn(v2, v3), __dmul_rn(G_kf, Y));   // never -0 (v2 - v3 is +0 when it vanishes), so 0.0 + dv == dv
+    } else {
+      // w = v2 - v3 = A/B - C/D with one reciprocal: (A*D - C*B) / (B*D)
+      const double z2 = Z * Z, y2 = Y * Y, z4 = z2 * z2;
+      const double A = G_VM2 * z2, B = k.k2n + z2;
+      const double Cn = (G_VM3 * y2) * z4, Dn = (k.krm + y2) * (k.kap + z4);
+      const double w = (A * Dn - Cn * B) * rcp_fast(B * Dn);
+      du += ((b - w) + Y) - G_k * Z;
+      dv = w - Y;
+    }
+  }
+}
+
+// ---- state access: plain vector, or sum_j c_j x_j formed on the fly (same operation order as lincomb_kernel) ---
+template <bool LC>
+__device__ __forceinline__ double2 state2(const RhsArgs &a, long long p) {
+  if constexpr (!LC) {
+    return reinterpret_cast<const double2 *>(a.y)[p];
+  } else {
+    double2 v[kMaxLc];
+#pragma unroll
+    for (int j = 0; j < kMaxLc; ++j)
+      v[j] = (j < a.nlc) ? reinterpret_cast<const double2 *>(a.lc_x[j])[p] : make_double2(0.0, 0.0);
+    double2 s = make_double2(a.lc_c[0] * v[0].x, a.lc_c[0] * v[0].y);
+#pragma unroll
+    for (int j = 1; j < kMaxLc; ++j)
+      if (j < a.nlc) { s.x = fma(a.lc_c[j], v[j].x, s.x); s.y = fma(a.lc_c[j], v[j].y, s.y); }
+    return s;
+  }
+}
+template <bool LC>
+__device__ __forceinline__ double stateu(const RhsArgs &a, long long p) {
+  if constexpr (!LC) {
+    return a.y[2 * p];
+  } else {
+    double v[kMaxLc];
+#pragma unroll
+    for (int j = 0; j < kMaxLc; ++j) v[j] = (j < a.nlc) ? a.lc_x[j][2 * p] : 0.0;
+    double s = a.lc_c[0] * v[0];
+#pragma unroll
+    for (int j = 1; j < kMaxLc; ++j)
+      if (j < a.nlc) s = fma(a.lc_c[j], v[j], s);
+    return s;
+  }
+}
+// u of the row below / above the launch's rows at column i
+template <bool LC>
+__device__ __forceinline__ double ghost_u(const RhsArgs &a, const double *ptr, long long off, long long i) {
+  if (!LC || ptr) return ptr[2 * i];
+  return stateu<true>(a, off + i);
+}
+
+// ---- the fused kernel ---------------------------------------------------------------------------------
+// work item = (row group jg, column i); rows j0 = jg*RY .. j0+RY-1 of the slab described by `a`.
+template <int MODEL, bool EXACT, int RY, int MINB, bool LC>
+__global__ void __launch_bounds__(256, MINB) rhs_kernel(const RhsArgs a) {
+  const long long nx = a.nx, nyl = a.nyl;
+  const long long w = blockIdx.x * 256LL + threadIdx.x;
+  const long long ngroups = (nyl + RY - 1) / RY;
+  if (w >= nx * ngroups) return;
+  // w / nx: multiply-shift when the work count fits 31 bits (host-computed magic), else 64-bit division
+  const long long jg = a.div_shift >= 0 ? (long long)((__umulhi(a.div_magic, (unsigned)w) + (unsigned)w) >> a.div_shift) : w / nx;
+  const long long i = w - jg * nx;
+  const long long j0 = jg * RY;
+  const long long iw = (i == 0) ? nx - 1 : i - 1;
+  const long long ie = (i == nx - 1) ? 0 : i + 1;
+  const int nrows = (nyl - j0 < RY) ? (int)(nyl - j0) : RY;
+
+  double2 c[RY];
+  double uw[RY], ue[RY];
+  double uu[RY + 2];  // u of rows j0-1 .. j0+RY
+#pragma unroll
+  for (int r = 0; r < RY; ++r) {
+    if (r < nrows) {
+      const long long row = (j0 + r) * nx;
+      c[r] = state2<LC>(a, row + i);
+      uw[r] = stateu<LC>(a, row + iw);
+      ue[r] = stateu<LC>(a, row + ie);
+    } else {
+      c[r] = make_double2(0.0, 0.0); uw[r] = 0.0; ue[r] = 0.0;
+    }
+  }
+  uu[0] = (j0 == 0) ? ghost_u<LC>(a, a.south, a.south_off, i) : stateu<LC>(a, (j0 - 1) * nx + i);
+  {
+    const long long jn = j0 + nrows;  // row above the last one this thread computes
+    uu[RY + 1] = (jn == nyl) ? ghost_u<LC>(a, a.north, a.north_off, i) : stateu<LC>(a, jn * nx + i);
+  }
+#pragma unroll
+  for (int r = 0; r < RY; ++r) uu[r + 1] = c[r].x;
+
+  double t1 = 0.0, t3 = 0.0;
+  if (is_torus(MODEL)) {
+    const double2 tc = reinterpret_cast<const double2 *>(a.cth)[i];
+    t1 = tc.x; t3 = tc.y;
+  }
+  double2 *__restrict__ out = reinterpret_cast<double2 *>(a.ydot);
+#pragma unroll
+  for (int r = 0; r < RY; ++r) {
+    if (r < nrows) {
+      const long long jl = j0 + r;
+      const double uN = (r + 1 == nrows) ? uu[RY + 1] : uu[r + 2];
+      const double uS = uu[r];
+      double du = EXACT ? stencil_exact<MODEL>(a.k, t1, t3, c[r].x, uw[r], ue[r], uS, uN)
+                        : stencil_fast<MODEL>(a.k, t1, t3, c[r].x, uw[r], ue[r], uS, uN);
+      double dv = 0.0;
+      if (a.react) {
+        const bool frozen = (a.freeze_north && jl == nyl - 1) || (a.freeze_south && jl == 0);
+        if (frozen) { du = 0.0; dv = 0.0; }
+        else react<MODEL, EXACT>(a.k, a.brow[jl], c[r].x, c[r].y, du, dv);
+      }
+      out[jl * nx + i] = make_double2(du, dv);
+    }
+  }
+}
+
+// Out-of-line recomputation of one thread's tile column with IEEE divisions (numerators in the subnormal /
+// huge / non-finite range somewhere in the column).  col points at the centre of the thread's first row.
+template <int MODEL>
+__device__ __noinline__ void redo_column_ieee(double Diff, double inv_rr, double twodx, double dxdx, double dydy, double k2n,
+                                              double krm, double kap, int react_on, const double2 *col, int pitch, int nrows,
+                                              double a1, double a3, const double *brow, double2 *out, long long nx) {
+  // scalars by value: taking the address of the kernel parameter block would force every thread to spill it
+  RhsConst k;
+  k.Diff = Diff; k.inv_rr = inv_rr; k.twodx = twodx; k.dxdx = dxdx; k.dydy = dydy; k.k2n = k2n; k.krm = krm; k.kap = kap;
+  for (int r = 0; r < nrows; ++r) {
+    const double2 cc = col[r * pitch];
+    const double uW = col[r * pitch - 1].x, uE = col[r * pitch + 1].x, uS = col[(r - 1) * pitch].x, uN = col[(r + 1) * pitch].x;
+    const double two_uC = __dmul_rn(2.0, cc.x);
+    const double n1 = __dmul_rn(Diff, __dmul_rn(a1, __dsub_rn(uE, uW)));
+    const double n2 = __dmul_rn(Diff, __dmul_rn(inv_rr, __dadd_rn(__dsub_rn(uE, two_uC), uW)));
+    const double n3 = __dmul_rn(Diff, __dmul_rn(a3, __dadd_rn(__dsub_rn(uN, two_uC), uS)));
+    double du = __dadd_rn(__dadd_rn(__ddiv_rn(n1, twodx), __ddiv_rn(n2, dxdx)), __ddiv_rn(n3, dydy));
+    double dv = 0.0;
+    if (react_on) react<MODEL, true>(k, brow[r], cc.x, cc.y, du, dv);
+    out[r * nx] = make_double2(du, dv);
+  }
+}
+
+// ---- the tiled kernel: row segments staged in shared memory by 1-D TMA bulk copies ---------------------
+// One CTA = one tile of TX theta columns x TY phi rows.  An elected thread arms an mbarrier with the tile's
+// byte count and issues one cp.async.bulk (UBLKCP) per tile row: (TX+2) points of rows j0-1 .. j0+TY, the
+// wrap columns and the ghost rows as separate small copies.  No thread computes a global load address for
+// the state; the stencil reads its neighbours from shared memory at compile-time offsets, the column's
+// previous/next row stay in registers while it marches, results leave as coalesced 16-byte stores.
+// Resident CTAs of the same SM overlap each other's load / compute / store phases.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, bool LC, int NG>
+__global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
+  constexpr int PITCH = TX + 2;            // points per staged row (west halo + TX + east halo)
+  constexpr int RPT = TY * TX / 256;       // rows marched by one thread
+  // NG: row groups the tile arrives in (one mbarrier each)
+  constexpr int GR = (TY + 2 + NG - 1) / NG;
+  static_assert(256 % TX == 0 && (TY * TX) % 256 == 0, "tile shape");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double2 *tile = reinterpret_cast<double2 *>(smem_raw);                      // [TY+2][PITCH]
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)(TY + 2) * PITCH * 16);
+
+  const long long nx = a.nx, nyl = a.nyl;
+  const long long tiles_x = (nx + TX - 1) / TX;
+  const long long ty = blockIdx.x / tiles_x;
+  const long long tx = blockIdx.x - ty * tiles_x;
+  const long long i0 = tx * TX, j0 = ty * TY;
+  const int w = (nx - i0 < TX) ? (int)(nx - i0) : TX;            // valid columns of this tile
+  const int h = (nyl - j0 < TY) ? (int)(nyl - j0) : TY;          // valid rows of this tile
+  const unsigned bar = smem_u32(mbar);
+
+  if (!LC) {
+  if (threadIdx.x == 0) {
+    // the staged rows arrive in NG groups, each on its own mbarrier, so the march starts when the first
+    // group has landed instead of waiting for the whole tile
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8u * gi) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const bool west_in = i0 > 0, east_in = i0 + w < nx;           // halo column contiguous with the tile?
+    const unsigned row_bytes = (unsigned)(w + (west_in ? 1 : 0) + (east_in ? 1 : 0)) * 16u;
+    const double2 *y2 = reinterpret_cast<const double2 *>(a.y);
+    for (int gi = 0; gi < NG; ++gi) {
+      const int ra = gi * GR, rb = (ra + GR < h + 2) ? ra + GR : h + 2;
+      const unsigned gbytes = (rb > ra) ? (unsigned)(rb - ra) * (unsigned)(w + 2) * 16u : 0u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar + 8u * gi), "r"(gbytes) : "memory");
+      for (int r = ra; r < rb; ++r) {
+        const long long jr = j0 - 1 + r;
+        const double2 *row = (jr < 0) ? reinterpret_cast<const double2 *>(a.south)
+                           : (jr >= nyl) ? reinterpret_cast<const double2 *>(a.north) : y2 + jr * nx;
+        const unsigned dst = smem_u32(tile + r * PITCH);
+        bulk_g2s(dst + (west_in ? 0u : 16u), row + i0 - (west_in ? 1 : 0), row_bytes, bar + 8u * gi);
+        if (!west_in) bulk_g2s(dst, row + (nx - 1), 16u, bar + 8u * gi);                    // theta wrap: column nx-1
+        if (!east_in) bulk_g2s(dst + (unsigned)(w + 1) * 16u, row, 16u, bar + 8u * gi);     // theta wrap: column 0
+      }
+    }
+  }
+  __syncthreads();   // barrier initialised before anyone polls it
+  } else {
+    // fused stage assembly: the tile is the combination sum_j c_j x_j, formed while it is staged (the stage
+    // state is never written to HBM).  Plain coalesced 16-byte loads; each thread stages its own column, nine
+    // rows per pass (9 loads per input vector in flight per thread), then the few halo-column entries.
+    auto generic = [&](int r, int sc) {
+      const long long jr = j0 - 1 + r;
+      const long long col = (sc == 0) ? (i0 == 0 ? nx - 1 : i0 - 1) : (sc == w + 1) ? (i0 + w == nx ? 0 : i0 + w) : i0 + sc - 1;
+      double2 v;
+      if (jr < 0) v = a.south ? reinterpret_cast<const double2 *>(a.south)[col] : state2<true>(a, a.south_off + col);
+      else if (jr >= nyl) v = a.north ? reinterpret_cast<const double2 *>(a.north)[col] : state2<true>(a, a.north_off + col);
+      else v = state2<true>(a, jr * nx + col);
+      tile[r * PITCH + sc] = v;
+    };
+    const int r_lo = (j0 == 0) ? 1 : 0, r_hi = (j0 + h == nyl) ? h + 1 : h + 2;   // tile rows that are rows of this launch
+    constexpr int R = 9;   // (TY + 2) = 18 rows in two passes, 9 loads per input vector in flight per thread
+    for (int tcol = threadIdx.x; tcol < w; tcol += 256) {
+      const long long p0 = (j0 - 1) * nx + i0 + tcol;   // point offset of tile row 0 in this column
+      for (int rb = r_lo; rb < r_hi; rb += R) {
+        double2 acc[R], v[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+          v[rr] = (rb + rr < r_hi) ? reinterpret_cast<const double2 *>(a.lc_x[0])[p0 + (rb + rr) * nx] : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) acc[rr] = make_double2(a.lc_c[0] * v[rr].x, a.lc_c[0] * v[rr].y);
+#pragma unroll
+        for (int j = 1; j < kMaxLc; ++j) {
+          if (j < a.nlc) {
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+              v[rr] = (rb + rr < r_hi) ? reinterpret_cast<const double2 *>(a.lc_x[j])[p0 + (rb + rr) * nx] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) { acc[rr].x = fma(a.lc_c[j], v[rr].x, acc[rr].x); acc[rr].y = fma(a.lc_c[j], v[rr].y, acc[rr].y); }
+          }
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+          if (rb + rr < r_hi) tile[(rb + rr) * PITCH + tcol + 1] = acc[rr];
+      }
+      if (r_lo == 1) generic(0, tcol + 1);          // ghost row below the slab
+      if (r_hi == h + 1) generic(h + 1, tcol + 1);  // ghost row above the slab
+    }
+    for (int e = threadIdx.x; e < 2 * (h + 2); e += 256) generic(e >> 1, (e & 1) ? w + 1 : 0);   // halo columns
+    __syncthreads();
+  }
+
+  const int c = (TX == 256) ? threadIdx.x : threadIdx.x % TX;   // column inside the tile
+  const int g0 = (TX == 256) ? 0 : (threadIdx.x / TX) * RPT; // first tile row of this thread (256 threads per CTA)
+  double t1 = 0.0, t3 = 0.0;
+  const bool active = c < w && g0 < h;
+  if (is_torus(MODEL) && active) {
+    const double2 tc = reinterpret_cast<const double2 *>(a.cth)[i0 + c];
+    t1 = tc.x; t3 = tc.y;
+  }
+  auto wait_group = [&](int gi) {   // phase 0 of group gi's barrier
+    unsigned ok = 0;
+    while (!ok) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(bar + 8u * gi) : "memory");
+    }
+  };
+  // rows g0, g0+1, g0+2 of the tile are needed before the first output row
+  if (!LC) {
+    for (int gi = 0; gi <= (g0 + 2) / GR; ++gi) wait_group(gi);
+  }
+  if (!active) return;
+
+  const double2 *col = tile + (g0 + 1) * PITCH + (c + 1);   // centre of this thread's first row
+  double uS = col[-PITCH].x;
+  double2 cc = col[0];
+  double2 *out = reinterpret_cast<double2 *>(a.ydot) + (j0 + g0) * nx + (i0 + c);
+  const int nrows = (h - g0 < RPT) ? (h - g0) : RPT;
+  const double *__restrict__ brow = a.brow + (j0 + g0);
+  const int react_on = a.react;
+  double2 *const out0 = out;
+  bool bad = (ACC && EXACT && is_torus(MODEL)) ? (a.k.div_safe == 0) : false;
+  auto row = [&](int r) {
+    if (!LC && r > 0 && (g0 + r + 2) % GR == 0 && (g0 + r + 2) / GR < NG) wait_group((g0 + r + 2) / GR);   // north row enters a new group
+    const double2 nn = col[(r + 1) * PITCH];
+    const double uW = col[r * PITCH - 1].x, uE = col[r * PITCH + 1].x;
+    double du = !EXACT ? stencil_fast<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x)
+                : ACC  ? stencil_exact_acc<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x, bad)
+                       : stencil_exact<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x);
+    double dv = 0.0;
+    if (react_on) react<MODEL, EXACT>(a.k, __ldg(brow + r), cc.x, cc.y, du, dv);
+    *out = make_double2(du, dv);
+    out += nx;
+    uS = cc.x;
+    cc = nn;
+  };
+  if (nrows == RPT) {   // full tile: straight-line code, rows interleave
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) row(r);
+  } else {
+    for (int r = 0; r < nrows; ++r) row(r);
+  }
+  // rare fix-ups, after the marched rows (same thread, same addresses: program order)
+  if (ACC && EXACT && is_torus(MODEL) && bad)
+    redo_column_ieee<MODEL>(a.k.Diff, a.k.inv_rr, a.k.twodx, a.k.dxdx, a.k.dydy, a.k.k2n, a.k.krm, a.k.kap, react_on,
+                            tile + (g0 + 1) * PITCH + (c + 1), PITCH, nrows, t1, t3, brow, out0, nx);
+  if (react_on) {
+    // frozen rows while t < tBoundary (:643-653): only slab row 0 / nyl-1 can be one
+    if (a.freeze_south && j0 + g0 == 0) out0[0] = make_double2(0.0, 0.0);
+    const long long rn = nyl - 1 - (j0 + g0);
+    if (a.freeze_north && rn >= 0 && rn < nrows) out0[rn * nx] = make_double2(0.0, 0.0);
+  }
+}
+
+template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, bool LC, int NG>
+int launch_tile_lc(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+  const long long tiles = ((a.nx + TX - 1) / TX) * ((a.nyl + TY - 1) / TY);
+  if (tiles <= 0) return 0;
+  if (tiles > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
+  const size_t smem = (size_t)(TY + 2) * (TX + 2) * 16 + 8 * NG + 8;
+  auto kern = rhs_tile_kernel<MODEL, EXACT, TX, TY, MINB, ACC, LC, NG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+    attr_set = true;
+  }
+  kern<<<(unsigned)tiles, 256, smem, st>>>(a);
+  return check_launch(g->ctx, "rhs_tile_kernel");
+}
+template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, int NG = 3>
+int launch_tile(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+  return a.nlc > 0 ? launch_tile_lc<MODEL, EXACT, TX, TY, MINB, ACC, true, 1>(g, a, st)
+                   : launch_tile_lc<MODEL, EXACT, TX, TY, MINB, ACC, false, NG>(g, a, st);
+}
+
+// ---- the streaming kernel: persistent CTAs, rows flow through a shared-memory ring ------------------------
+// 2 CTAs per SM stay resident and walk over (strip of 256 columns) x (segment of rows) units.  Warp 8 is the
+// producer: one lane issues a 1-D TMA bulk copy per row and input vector into the next free ring slot and arms
+// that slot's "full" mbarrier with the byte count.  Warps 0..7 are consumers: a thread owns one column, waits for
+// the slot, reads (and, for a fused stage, combines sum_j c_j x_j of) its point and the two neighbours' u, releases
+// the slot on the "empty" mbarrier, and with the previous two rows still in registers computes the row before.
+// Every state row is fetched once (plus one halo row per segment end); no CTA start-up per tile.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok = 0;
+  while (!ok) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+
+template <int MODEL, bool EXACT, int NV, bool PLAIN, int RB>
+__global__ void __launch_bounds__(288, 2) rhs_stream_kernel(const RhsArgs a, int seg_rows, int S) {
+  constexpr int TX = 256, PITCH = TX + 2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double2 *ring = reinterpret_cast<double2 *>(smem_raw);                       // [S][RB][NV][PITCH]
+  const unsigned bars = smem_u32(smem_raw + (size_t)S * RB * NV * PITCH * 16); // full[S], empty[S]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long nx = a.nx, nyl = a.nyl;
+  const long long strips = (nx + TX - 1) / TX, segs = (nyl + seg_rows - 1) / seg_rows, units = strips * segs;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * s) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(bars + 8u * (S + s)) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 8) {   // ---------------- producer ----------------
+    if (lane != 0) return;
+    long long it = 0;   // stage counter
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const long long strip = u % strips, seg = u / strips;
+      const long long i0 = strip * TX, jA = seg * seg_rows, jB = (jA + seg_rows < nyl) ? jA + seg_rows : nyl;
+      const int w = (nx - i0 < TX) ? (int)(nx - i0) : TX;
+      const bool west_in = i0 > 0, east_in = i0 + w < nx;
+      const unsigned row_bytes = (unsigned)(w + (west_in ? 1 : 0) + (east_in ? 1 : 0)) * 16u;
+      for (long long j0 = jA - 1; j0 <= jB; j0 += RB, ++it) {   // a stage = rows j0 .. j0+RB-1 (clipped at jB)
+        const int s = (int)(it % S);
+        mbar_wait(bars + 8u * (S + s), (unsigned)((it / S) & 1) ^ 1u);
+        const int nr = (jB - j0 + 1 < RB) ? (int)(jB - j0 + 1) : RB;
+        unsigned bytes = 0;
+        for (int rr = 0; rr < nr; ++rr) {
+          const long long jr = j0 + rr;
+          const bool ext = (jr < 0 && a.south) || (jr >= nyl && a.north);
+          bytes += (unsigned)((PLAIN || ext) ? 1 : NV) * (unsigned)(w + 2) * 16u;
+        }
+        const unsigned full = bars + 8u * s;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
+        for (int rr = 0; rr < nr; ++rr) {
+          const long long jr = j0 + rr;
+          const bool ext = (jr < 0 && a.south) || (jr >= nyl && a.north);   // an already combined ghost row
+          const int nvec = (PLAIN || ext) ? 1 : NV;
+          for (int v = 0; v < nvec; ++v) {
+            const double2 *row;
+            if (ext) row = reinterpret_cast<const double2 *>(jr < 0 ? a.south : a.north);
+            else if (PLAIN) row = reinterpret_cast<const double2 *>(a.y) + jr * nx;
+            else {
+              const long long off = (jr < 0) ? a.south_off : (jr >= nyl) ? a.north_off : jr * nx;
+              row = reinterpret_cast<const double2 *>(a.lc_x[v]) + off;
+            }
+            const unsigned dst = smem_u32(ring + (((size_t)s * RB + rr) * NV + v) * PITCH);
+            bulk_g2s(dst + (west_in ? 0u : 16u), row + i0 - (west_in ? 1 : 0), row_bytes, full);
+            if (!west_in) bulk_g2s(dst, row + (nx - 1), 16u, full);
+            if (!east_in) bulk_g2s(dst + (unsigned)(w + 1) * 16u, row, 16u, full);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const int c = threadIdx.x;   // 0..255: column inside the strip
+  const int react_on = a.react;
+  long long it = 0;
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    const long long strip = u % strips, seg = u / strips;
+    const long long i0 = strip * TX, jA = seg * seg_rows, jB = (jA + seg_rows < nyl) ? jA + seg_rows : nyl;
+    const int w = (nx - i0 < TX) ? (int)(nx - i0) : TX;
+    const bool active = c < w;
+    double t1 = 0.0, t3 = 0.0;
+    if (is_torus(MODEL) && active) {
+      const double2 tc = reinterpret_cast<const double2 *>(a.cth)[i0 + c];
+      t1 = tc.x; t3 = tc.y;
+    }
+    double2 *out = reinterpret_cast<double2 *>(a.ydot) + jA * nx + (i0 + c);
+    double uS = 0.0, cW = 0.0, cE = 0.0;
+    double2 cc = make_double2(0.0, 0.0);
+    // one row: fetch (and combine) the arriving row jr, then emit row jr-1 from the three rows in registers
+    auto step = [&](const double2 *slot, long long jr) {
+      const bool ext = (jr < 0 && a.south) || (jr >= nyl && a.north);
+      double2 nn;
+      double nW, nE;
+      if (PLAIN || ext) {
+        nn = slot[c + 1]; nW = slot[c].x; nE = slot[c + 2].x;
+      } else {
+        double2 v[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = slot[j * PITCH + c + 1];
+        nn = make_double2(a.lc_c[0] * v[0].x, a.lc_c[0] * v[0].y);
+#pragma unroll
+        for (int j = 1; j < NV; ++j) { nn.x = fma(a.lc_c[j], v[j].x, nn.x); nn.y = fma(a.lc_c[j], v[j].y, nn.y); }
+        nW = __shfl_up_sync(0xffffffffu, nn.x, 1);
+        nE = __shfl_down_sync(0xffffffffu, nn.x, 1);
+        if (lane == 0 || lane == 31) {   // the neighbour lives in another warp: combine its u from the slot
+          const int q = (lane == 0) ? c : c + 2;
+          double e = a.lc_c[0] * slot[q].x;
+#pragma unroll
+          for (int j = 1; j < NV; ++j) e = fma(a.lc_c[j], slot[j * PITCH + q].x, e);
+          if (lane == 0) nW = e; else nE = e;
+        }
+      }
+      if (jr > jA) {   // rows jr-2 (uS), jr-1 (cc) and jr (nn) are here: output row jr-1
+        const long long jl = jr - 1;
+        double du = EXACT ? stencil_exact<MODEL>(a.k, t1, t3, cc.x, cW, cE, uS, nn.x)
+                          : stencil_fast<MODEL>(a.k, t1, t3, cc.x, cW, cE, uS, nn.x);
+        double dv = 0.0;
+        if (react_on) {
+          react<MODEL, EXACT>(a.k, __ldg(a.brow + jl), cc.x, cc.y, du, dv);
+          const bool frozen = (a.freeze_north && jl == nyl - 1) || (a.freeze_south && jl == 0);
+          du = frozen ? 0.0 : du;
+          dv = frozen ? 0.0 : dv;
+        }
+        if (active) *out = make_double2(du, dv);
+        out += nx;
+      }
+      uS = cc.x; cc = nn; cW = nW; cE = nE;
+    };
+    for (long long j0 = jA - 1; j0 <= jB; j0 += RB, ++it) {
+      const int s = (int)(it % S);
+      mbar_wait(bars + 8u * s, (unsigned)((it / S) & 1));
+      const double2 *stage = ring + (size_t)s * RB * NV * PITCH;
+      const int nr = (jB - j0 + 1 < RB) ? (int)(jB - j0 + 1) : RB;
+      if (nr == RB) {
+#pragma unroll
+        for (int rr = 0; rr < RB; ++rr) step(stage + (size_t)rr * NV * PITCH, j0 + rr);
+      } else {
+        for (int rr = 0; rr < nr; ++rr) step(stage + (size_t)rr * NV * PITCH, j0 + rr);
+      }
+      __syncwarp();   // every lane has read the stage (the values it still needs are in registers)
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8u * (S + s)) : "memory");
+    }
+  }
+}
+
+template <int MODEL, bool EXACT, int NV, bool PLAIN>
+int launch_stream_nv(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+  constexpr int RB = (NV == 1) ? 4 : (NV <= 3 ? 2 : 1);   // rows per ring stage
+  const int seg_rows = 128;
+  const long long strips = (a.nx + 255) / 256, segs = (a.nyl + seg_rows - 1) / seg_rows, units = strips * segs;
+  if (units <= 0) return 0;
+  const size_t stage_bytes = (size_t)RB * NV * 258 * 16;
+  int S = (int)(100000 / stage_bytes);
+  if (S > 8) S = 8;
+  if (S < 3) S = 3;
+  const size_t smem = (size_t)S * stage_bytes + (size_t)2 * S * 8;
+  auto kern = rhs_stream_kernel<MODEL, EXACT, NV, PLAIN, RB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110000);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+    attr_set = true;
+  }
+  const long long ctas = units < 2LL * kSMs ? units : 2LL * kSMs;
+  kern<<<(unsigned)ctas, 288, smem, st>>>(a, seg_rows, S);
+  return check_launch(g->ctx, "rhs_stream_kernel");
+}
+
+template <int MODEL, bool EXACT>
+int launch_stream(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+  switch (a.nlc) {
+    case 0: return launch_stream_nv<MODEL, EXACT, 1, true>(g, a, st);
+    case 2: return launch_stream_nv<MODEL, EXACT, 2, false>(g, a, st);
+    case 3: return launch_stream_nv<MODEL, EXACT, 3, false>(g, a, st);
+    case 5: return launch_stream_nv<MODEL, EXACT, 5, false>(g, a, st);
+    default: return 1;   // other counts: caller falls back to the tiled kernel
+  }
+}
+
+template <int MODEL, bool EXACT>
+int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
+  // variant 0 = automatic.  Large slabs (>= 4 Mi points, HBM-bound): the TMA-tiled kernel wherever a tile row is
+  // reasonably full.  Small slabs (the reference's default 400x1600 / 100x400 grids live in L2 and are bound by
+  // launch latency and by how many CTAs a partial wave gets): the direct kernel with 2 rows per thread.
+  // explicit: direct kernel (rows per thread, min CTAs/SM) 1 (2,4) | 2 (8,2) | 3 (1,4) | 4 (4,3) | 5 (4,4)
+  //           tiled kernel (TX, TY, min CTAs/SM) 10 (128,16,4) | 11 (128,32,3) | 12 (64,32,4) | 13 (256,16,3) | 14 (128,16,3)
+  //           15 = 13 with flag-and-redo instead of a branch per point
+  int variant = g->variant;
+  if (variant == 0) {
+    const long long pts = a_in.nx * a_in.nyl;
+    if (pts < (4LL << 20)) variant = 1;
+    else variant = (a_in.nx >= 192) ? ((EXACT && !is_fhn(MODEL)) ? 15 : 13) : (a_in.nx >= 96) ? 10 : 5;   // measured: profiles/README.md
+  }
+  // measured (profiles/README.md): the streaming kernel wins only for the widest fused stage (5 input vectors,
+  // where its once-per-row fetch beats the tiled kernel's register-staged tiles); the tiled kernel everywhere else
+  if (g->variant == 0 && a_in.nlc == 5 && a_in.nx >= 192 && a_in.nx * a_in.nyl >= (4LL << 20)) variant = 20;
+  if (variant == 20) {   // streaming kernel (persistent CTAs, shared-memory row ring)
+    const int r = launch_stream<MODEL, EXACT>(g, a_in, st);
+    if (r <= 0) return r;
+    variant = 13;
+  }
+  switch (variant) {
+    case 10: return launch_tile<MODEL, EXACT, 128, 16, 4, false>(g, a_in, st);
+    case 11: return launch_tile<MODEL, EXACT, 128, 32, 3, false>(g, a_in, st);
+    case 12: return launch_tile<MODEL, EXACT, 64, 32, 4, false>(g, a_in, st);
+    case 13: return launch_tile<MODEL, EXACT, 256, 16, 3, false>(g, a_in, st);
+    case 14: return launch_tile<MODEL, EXACT, 128, 16, 3, false>(g, a_in, st);
+    case 15: return launch_tile<MODEL, EXACT, 256, 16, 3, true>(g, a_in, st);   // flag-and-redo instead of a branch per point
+    case 16: return launch_tile<MODEL, EXACT, 256, 16, 3, false, 6>(g, a_in, st);  // tile arrives in 6 row groups
+    case 17: return launch_tile<MODEL, EXACT, 256, 16, 3, false, 2>(g, a_in, st);  // ... in 2
+    case 18: return launch_tile<MODEL, EXACT, 256, 16, 3, false, 9>(g, a_in, st);  // ... in 9
+    default: break;
+  }
+  const int RY = (variant == 1) ? 2 : (variant == 2) ? 8 : (variant == 3) ? 1 : 4;
+  const long long ngroups = (a_in.nyl + RY - 1) / RY;
+  const long long work = a_in.nx * ngroups;
+  const long long blocks = (work + 255) / 256;
+  if (blocks <= 0) return 0;
+  RhsArgs a = a_in;
+  a.div_shift = -1; a.div_magic = 0;
+  if (work < (1LL << 31)) {  // Granlund-Montgomery: n / d = (mulhi(m, n) + n) >> l for n < 2^31
+    int l = 0;
+    while ((1LL << l) < a.nx) ++l;
+    a.div_shift = l;
+    a.div_magic = (unsigned)((((1ULL << l) - (unsigned long long)a.nx) << 32) / (unsigned long long)a.nx + 1ULL);
+  }
+  if (blocks > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
+  const unsigned nb = (unsigned)blocks;
+  const bool lc = a.nlc > 0;
+#define CRD_DIRECT(RY_, MB_)                                                   \
+  do {                                                                         \
+    if (lc) rhs_kernel<MODEL, EXACT, RY_, MB_, true><<<nb, 256, 0, st>>>(a);   \
+    else rhs_kernel<MODEL, EXACT, RY_, MB_, false><<<nb, 256, 0, st>>>(a);     \
+  } while (0)
+  switch (variant) {
+    case 1: CRD_DIRECT(2, 4); break;
+    case 2: CRD_DIRECT(8, 2); break;
+    case 3: CRD_DIRECT(1, 4); break;
+    case 4: CRD_DIRECT(4, 3); break;
+    default: CRD_DIRECT(4, 4); break;
+  }
+#undef CRD_DIRECT
+  return check_launch(g->ctx, "rhs_kernel");
+}
+
+int launch_rhs(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+  const bool exact = g->p.arith == CRD_ARITH_EXACT;
+  switch (g->p.model) {
+    case CRD_FHN_TORUS: return exact ? launch_model<CRD_FHN_TORUS, true>(g, a, st) : launch_model<CRD_FHN_TORUS, false>(g, a, st);
+    case CRD_GOLDBETER_TORUS: return exact ? launch_model<CRD_GOLDBETER_TORUS, true>(g, a, st) : launch_model<CRD_GOLDBETER_TORUS, false>(g, a, st);
+    case CRD_FHN_FLAT: return exact ? launch_model<CRD_FHN_FLAT, true>(g, a, st) : launch_model<CRD_FHN_FLAT, false>(g, a, st);
+    case CRD_GOLDBETER_FLAT: return exact ? launch_model<CRD_GOLDBETER_FLAT, true>(g, a, st) : launch_model<CRD_GOLDBETER_FLAT, false>(g, a, st);
+  }
+  set_error("unknown model %d", g->p.model);
+  return -1;
+}
+
+// Arguments for rows [r0, r1) of the slab.  The rows just outside that range are given either as an external
+// pointer (ghost row) or as a row index of the slab itself.
+struct RowRef { const double *ptr; long long row; };
+inline RowRef ext_row(const double *p) { return RowRef{p, 0}; }
+inline RowRef slab_row(long long r) { return RowRef{nullptr, r}; }
+
+RhsArgs make_args(const crd_grid *g, double t, const StateRef &S, double *ydot, long long r0, long long r1, RowRef south,
+                  RowRef north) {
+  RhsArgs a;
+  const long long nx = g->nx;
+  a.nlc = S.n;
+  a.south_off = a.north_off = 0;
+  if (S.n == 0) {
+    a.y = S.y + 2 * r0 * nx;
+    a.south = south.ptr ? south.ptr : S.y + 2 * south.row * nx;
+    a.north = north.ptr ? north.ptr : S.y + 2 * north.row * nx;
+    for (int j = 0; j < kMaxLc; ++j) { a.lc_x[j] = nullptr; a.lc_c[j] = 0.0; }
+  } else {
+    a.y = nullptr;
+    for (int j = 0; j < kMaxLc; ++j) {
+      a.lc_x[j] = j < S.n ? S.x[j] + 2 * r0 * nx : nullptr;
+      a.lc_c[j] = j < S.n ? S.c[j] : 0.0;
+    }
+    a.south = south.ptr; a.south_off = (south.row - r0) * nx;
+    a.north = north.ptr; a.north_off = (north.row - r0) * nx;
+  }
+  a.ydot = ydot + 2 * r0 * nx;
+  a.cth = g->cth;
+  a.brow = g->brow + r0;
+  a.nx = nx;
+  a.nyl = r1 - r0;
+  const bool tb = t < g->p.t_boundary;
+  a.freeze_south = (tb && g->js == 0 && r0 == 0) ? 1 : 0;
+  a.freeze_north = (tb && g->je == g->ny - 1 && r1 == g->nyl) ? 1 : 0;
+  a.react = (is_fhn(g->p.model) || g->p.just_diffusion == 0) ? 1 : 0;
+  a.div_shift = -1; a.div_magic = 0;
+  a.k = g->k;
+  return a;
+}
+
+// ---- halo ring: push first/last row into the neighbours' ghost blocks, flag the epoch ------------------
+template <bool LC>
+__global__ void __launch_bounds__(256) halo_push_kernel(const RhsArgs a, double *prev_north, double *next_south,
+                                                        unsigned long long *prev_flag, unsigned long long *next_flag,
+                                                        unsigned long long *ticket, unsigned long long epoch) {
+  const long long nx = a.nx, nyl = a.nyl;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double2 *pn = reinterpret_cast<double2 *>(prev_north), *ns = reinterpret_cast<double2 *>(next_south);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nx; i += stride) {
+    pn[i] = state2<LC>(a, i);                     // my row js is the row above prev's je
+    ns[i] = state2<LC>(a, (nyl - 1) * nx + i);    // my row je is the row below next's js
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long done = atomicAdd(ticket, 1ULL) + 1ULL;
+    if (done == gridDim.x * epoch) {  // last block of this epoch (ticket is never reset)
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(prev_flag), "l"(epoch) : "memory");
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(next_flag), "l"(epoch) : "memory");
+    }
+  }
+}
+
+__global__ void halo_wait_kernel(const unsigned long long *flag_south, const unsigned long long *flag_north,
+                                 unsigned long long epoch, int *err) {
+  const unsigned long long *f = threadIdx.x == 0 ? flag_south : flag_north;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    if (v >= epoch) break;
+    if (clock64() - t0 > 6000000000LL) {  // ~3 s: a neighbour never posted; report instead of hanging
+      *err = 100 + (int)threadIdx.x;
+      __threadfence_system();
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+
+constexpr int kPushBlocks = 16;
+
+// ---- initial conditions -----------------------------------------------------------------------------------
+struct IcArgs {
+  int model, vary_beta, wave_inside, ic_type;
+  long long nx, nyl, js;
+  double dx, dy, xmin, ymin;
+  double wave_length, wave_width, wave_xmin, wave_xmax;
+  double s0, s1, p0, p1;  // steady state, perturbed state
+};
+
+__global__ void __launch_bounds__(256) ic_kernel(const IcArgs a, double2 *__restrict__ y) {
+  const long long w = blockIdx.x * 256LL + threadIdx.x;
+  if (w >= a.nx * a.nyl) return;
+  const long long j = w / a.nx, i = w - j * a.nx;
+  const double yy = __dadd_rn(a.ymin, __dmul_rn((double)(a.js + j), a.dy));
+  const double xx = __dadd_rn(a.xmin, __dmul_rn((double)i, a.dx));
+  double2 v;
+  const bool fhn = is_fhn(a.model), torus = is_torus(a.model);
+  if (a.vary_beta == 0) {
+    bool in;
+    if (torus) {
+      const bool ybox = yy >= a.wave_length && yy <= __dmul_rn(2.0, a.wave_length);
+      if (a.wave_inside == 1) in = xx >= a.wave_xmin && xx <= a.wave_xmax && ybox;
+      else in = (xx >= a.wave_xmin || xx <= a.wave_xmax) && ybox;
+    } else if (fhn) {
+      in = xx >= a.wave_xmin && xx <= a.wave_xmax && yy >= a.wave_length && yy <= __dmul_rn(2.0, a.wave_length);
+    } else {
+      in = xx >= a.wave_xmin && xx <= a.wave_xmax && yy >= __dmul_rn(2.0, a.wave_length) && yy <= __dmul_rn(3.0, a.wave_length);
+    }
+    v = in ? make_double2(a.p0, a.p1) : make_double2(a.s0, a.s1);
+  } else if (fhn) {
+    v = make_double2(1.0, 1.0);
+  } else {
+    v = make_double2(0.4, 1.6);
+    if (a.ic_type == 1) {
+      const bool in = xx >= a.wave_xmin && xx <= a.wave_xmax && yy >= __dmul_rn(2.0, a.wave_length) && yy <= __dmul_rn(3.0, a.wave_length);
+      if (in) v = make_double2(1.4, 2.6);
+    }
+  }
+  y[w] = v;
+}
+
+}  // namespace
