@@ -168,7 +168,7 @@ def cpu_baseline(model="fhn_torus", NX=NX, budget_s=20.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="crd")
     ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
