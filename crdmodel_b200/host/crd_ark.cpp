@@ -473,6 +473,11 @@ int ARKode(void *mem, realtype tout, N_Vector yout, realtype *tret, int itask) {
 void ARKodeFree(void **mem) {
   if (!mem || !*mem) return;
   ArkMem *m = (ArkMem *)*mem;
+  // the reference never queries the counters; CRD_ARK_STATS=1 prints them when the integrator is freed
+  if (const char *e = std::getenv("CRD_ARK_STATS"))
+    if (e[0] == '1')
+      std::fprintf(stderr, "crd_ark: nst = %ld, attempts = %ld, nfe = %ld, netf = %ld, t = %.17g\n", m->nst, m->nst_attempts, m->nfe,
+                   m->netf, m->tn);
   free_vectors(m);
   delete m;
   *mem = nullptr;
