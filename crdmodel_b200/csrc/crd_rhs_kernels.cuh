@@ -467,11 +467,12 @@ int launch_tile_lc(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   if (tiles > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
   const size_t smem = (size_t)(TY + 2) * (TX + 2) * 16 + 8 * NG + 8;
   auto kern = rhs_tile_kernel<MODEL, EXACT, TX, TY, MINB, ACC, LC, NG>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};   // the attribute is per device
+  const int dev = g->ctx->device & 63;
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
-    attr_set = true;
+    attr_set[dev] = true;
   }
   kern<<<(unsigned)tiles, 256, smem, st>>>(a);
   return check_launch(g->ctx, "rhs_tile_kernel");
@@ -646,11 +647,12 @@ int launch_stream_nv(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   if (S < 3) S = 3;
   const size_t smem = (size_t)S * stage_bytes + (size_t)2 * S * 8;
   auto kern = rhs_stream_kernel<MODEL, EXACT, NV, PLAIN, RB>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};   // the attribute is per device
+  const int dev = g->ctx->device & 63;
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110000);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const long long ctas = units < 2LL * kSMs ? units : 2LL * kSMs;
   kern<<<(unsigned)ctas, 288, smem, st>>>(a, seg_rows, S);
