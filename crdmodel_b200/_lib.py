@@ -30,7 +30,7 @@ class IcParams(C.Structure):
 
 
 class FusedOps(C.Structure):
-    _fields_ = [("lincomb", C.c_void_p), ("erk_finish", C.c_void_p), ("rhs_lincomb", C.c_void_p)]
+    _fields_ = [("lincomb", C.c_void_p), ("erk_finish", C.c_void_p), ("rhs_lincomb", C.c_void_p), ("erk_evolve", C.c_void_p)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, c_double_p, C.c_int, C.c_int, C.c_void_p)
@@ -79,6 +79,9 @@ SIGNATURES = {
     "crd_grid_rhs_count": (C.c_int64, [P]),
     "crd_grid_set_variant": (I, [P, I]),
     "crd_grid_set_overlap": (I, [P, I]),
+    "crd_erk_evolve": (I, [P, P]),
+    "crd_grid_set_resident": (I, [P, I]),
+    "crd_grid_resident_launches": (C.c_int64, [P]),
     "crd_fill_synthetic": (I, [P, I, C.c_uint64, C.c_int64, C.c_int64, P]),
     "crd_fill_initial_conditions": (I, [P, C.POINTER(IcParams), P]),
     # device N_Vector
@@ -158,6 +161,7 @@ SIGNATURES = {
     "ARKodeGetCurrentTime": (I, [P, c_double_p]),
     "crd_ARKodeSetFusedOps": (I, [P, P]),
     "crd_ARKodeSetReuseFirstStage": (I, [P, I]),
+    "crd_ARKodeSetResident": (I, [P, I]),
     "crd_ARKodeSetInitStep": (I, [P, D]),
     "crd_ARKodeSetFixedStep": (I, [P, D]),
 }

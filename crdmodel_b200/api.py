@@ -231,6 +231,14 @@ class Grid:
     def set_variant(self, v):
         check(lib().crd_grid_set_variant(self._h, v), "crd_grid_set_variant")
 
+    def set_resident(self, mode):
+        """Device-resident step loop: 0 automatic (meshes of up to 4 Mi points), 1 whenever it applies, -1 never."""
+        check(lib().crd_grid_set_resident(self._h, mode), "crd_grid_set_resident")
+
+    @property
+    def resident_launches(self):
+        return lib().crd_grid_resident_launches(self._h)
+
     def set_overlap(self, on):
         check(lib().crd_grid_set_overlap(self._h, 1 if on else 0), "crd_grid_set_overlap")
 
@@ -279,7 +287,8 @@ class Grid:
 class ARKodeSolver:
     """The reference's ARKode call sequence (FHNmodel_torus.cpp:356-373,423,491) over the device path."""
 
-    def __init__(self, grid, y, t0=0.0, rtol=1e-5, atol=1e-10, max_steps=200000, fused=True, reuse_first_stage=False):
+    def __init__(self, grid, y, t0=0.0, rtol=1e-5, atol=1e-10, max_steps=200000, fused=True, reuse_first_stage=False,
+                 resident=True):
         L = lib()
         self.grid, self.y = grid, y
         self.mem = C.c_void_p(check_ptr(L.ARKodeCreate(), "ARKodeCreate"))
@@ -294,6 +303,9 @@ class ARKodeSolver:
             table = L.crd_nv_fused_vector_ops() if fused == "ops" else L.crd_nv_fused_ops()
             check(L.crd_ARKodeSetFusedOps(self.mem, C.cast(table, C.c_void_p)), "crd_ARKodeSetFusedOps")
         check(L.crd_ARKodeSetReuseFirstStage(self.mem, 1 if reuse_first_stage else 0), "crd_ARKodeSetReuseFirstStage")
+        # resident: with the full fused table the whole step loop runs as one persistent kernel when it applies
+        # (one GPU, mesh within the grid's size limit: Grid.set_resident); False keeps one launch per stage
+        check(L.crd_ARKodeSetResident(self.mem, 1 if resident else 0), "crd_ARKodeSetResident")
 
     def set_init_step(self, h):
         check(lib().crd_ARKodeSetInitStep(self.mem, h), "crd_ARKodeSetInitStep")

@@ -89,6 +89,12 @@ struct crd_grid {
   unsigned long long computed = 0;   // epoch of the last compute
   int64_t rhs_count = 0;
   int variant = 0;
+  // device-resident step loop (crd_resident.cu): -1 off, 0 automatic (meshes that live in L2), 1 always
+  int resident = 0;
+  int64_t resident_launches = 0;
+  unsigned long long *res_bar = nullptr;
+  double *res_partial = nullptr;
+  void *res_out_host = nullptr, *res_out_dev = nullptr;
   // overlap of the halo exchange with the interior rows (auxiliary stream)
   bool overlap = true, split = false;
   cudaStream_t s_aux = nullptr;

@@ -13,6 +13,7 @@
 #include <new>
 
 #include "crd_common.cuh"
+#include "crd_fused.cuh"
 
 using namespace crd;
 
@@ -273,28 +274,7 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LinCombArgs a, doubl
   }
 }
 
-// ---- fused: ynew = yn + sum hb_j F_j ; err = sum hd_j F_j ; two weighted square sums ------------------------
-struct FinishArgs {
-  const double *F[CRD_ARK_MAX_LINCOMB];
-  double hb[CRD_ARK_MAX_LINCOMB], hd[CRD_ARK_MAX_LINCOMB];
-  const double *yn;
-  double *ynew;
-  double rtol, atol;
-};
-
-template <int S>
-__device__ __forceinline__ void finish_elem(const FinishArgs &a, const double yn, const double (&f)[S], double &ynew, double &e2, double &y2) {
-  double s = yn, err = 0.0;
-#pragma unroll
-  for (int j = 0; j < S; ++j) { s = fma(a.hb[j], f[j], s); err = fma(a.hd[j], f[j], err); }
-  ynew = s;
-  const double w = 1.0 / fma(a.rtol, fabs(yn), a.atol);
-  const double wn = 1.0 / fma(a.rtol, fabs(s), a.atol);
-  const double pe = err * w, py = s * wn;
-  e2 += pe * pe;
-  y2 += py * py;
-}
-
+// ---- fused: ynew = yn + sum hb_j F_j ; err = sum hd_j F_j ; two weighted square sums (crd_fused.cuh) ----------
 template <int S>
 __global__ void __launch_bounds__(kRedThreads) erk_finish_kernel(const FinishArgs a, long long n, double *partial,
                                                                  unsigned int *ticket, double *result) {
@@ -335,8 +315,8 @@ struct _generic_N_Vector_Ops g_ops = {
     N_VDotProd_Crd, N_VMaxNorm_Crd, N_VWrmsNorm_Crd, N_VWrmsNormMask_Crd, N_VMin_Crd, N_VWL2Norm_Crd, N_VL1Norm_Crd,
     N_VCompare_Crd, N_VInvTest_Crd, N_VConstrMask_Crd, N_VMinQuotient_Crd};
 
-const crd_fused_ops g_fused = {N_VLinearCombination_Crd, N_VErkFinish_Crd, crd_f_lincomb};
-const crd_fused_ops g_fused_ops_only = {N_VLinearCombination_Crd, N_VErkFinish_Crd, nullptr};
+const crd_fused_ops g_fused = {N_VLinearCombination_Crd, N_VErkFinish_Crd, crd_f_lincomb, crd_erk_evolve};
+const crd_fused_ops g_fused_ops_only = {N_VLinearCombination_Crd, N_VErkFinish_Crd, nullptr, nullptr};
 
 }  // namespace
 

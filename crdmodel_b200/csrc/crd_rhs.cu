@@ -114,6 +114,9 @@ void crd_grid_destroy(crd_grid *g) {
   if (g->prev_ipc && g->halo_prev) cudaIpcCloseMemHandle(g->halo_prev);
   if (g->next_ipc && g->halo_next && g->halo_next != g->halo_prev) cudaIpcCloseMemHandle(g->halo_next);
   cudaFree(g->cth); cudaFree(g->brow); cudaFree(g->halo_local); cudaFree(g->push_ticket);
+  if (g->res_bar) cudaFree(g->res_bar);
+  if (g->res_partial) cudaFree(g->res_partial);
+  if (g->res_out_host) cudaFreeHost(g->res_out_host);
   if (g->stage_y) cudaFree(g->stage_y);
   if (g->stage_ydot) cudaFree(g->stage_ydot);
   if (g->s_in) cudaStreamDestroy(g->s_in);

@@ -60,6 +60,8 @@ struct ArkMem {
   long nglobal = 0;
   const crd_fused_ops *fused = nullptr;
   bool reuse_first = false;
+  bool resident = true;     // use fused->erk_evolve when it is offered and applies
+  bool resident_na = false; // it answered "does not apply" once: stop asking
 };
 
 void set_zonneveld(ArkMem *m) {
@@ -312,6 +314,47 @@ int dense_eval(ArkMem *m, double t, N_Vector yout) {
   return 0;
 }
 
+// Hand the loop to the vector implementation (crd_fused_ops.erk_evolve).  Returns EVOLVE_NA when it does not apply,
+// otherwise what the host loop would return before its dense-output evaluation.
+constexpr int EVOLVE_NA = 12345;
+int evolve_resident(ArkMem *m, double tout, int itask) {
+  if (m->s > CRD_ERK_MAX_STAGES) return EVOLVE_NA;
+  // the "too much accuracy" test of the first step needs the norm the fused finish supplies from then on
+  if (m->ynorm_sq_next < 0) {
+    double nrm = N_VWrmsNorm(m->yn, m->ewt);
+    m->ynorm_sq_next = nrm * nrm * (double)m->nglobal;
+  }
+  crd_erk_state st;
+  std::memset(&st, 0, sizeof st);
+  st.s = m->s; st.p = m->p;
+  for (int i = 0; i < m->s; ++i) {
+    for (int j = 0; j < m->s; ++j) st.A[i][j] = m->A[i][j];
+    st.b[i] = m->b[i]; st.d[i] = m->b[i] - m->b2[i]; st.c[i] = m->c[i];
+  }
+  st.rtol = m->rtol; st.atol = m->atol;
+  st.k1 = m->k1; st.k2 = m->k2; st.k3 = m->k3; st.bias = m->bias; st.safety = m->safety; st.growth = m->growth;
+  st.etamxf = m->etamxf; st.etamin = m->etamin; st.lbound = m->lbound; st.ubound = m->ubound;
+  st.small_nef = m->small_nef; st.maxnef = m->maxnef;
+  st.nglobal = m->nglobal;
+  st.tout = tout; st.itask = itask; st.max_steps = m->mxstep;
+  st.tn = m->tn; st.next_h = m->next_h; st.hold = m->hold; st.eta = m->eta; st.etamax = m->etamax;
+  st.ehist[0] = m->ehist[0]; st.ehist[1] = m->ehist[1];
+  st.ynorm_sq = m->ynorm_sq_next;
+  st.nst = m->nst; st.nst_attempts = m->nst_attempts; st.nfe = m->nfe; st.netf = m->netf;
+  st.yn = m->yn; st.yold = m->yold; st.ycur = m->ycur; st.fnew = m->fnew; st.fold = m->fold;
+  for (int i = 0; i < m->s; ++i) st.F[i] = m->F[i];
+  int r = m->fused->erk_evolve(&st, m->user_data);
+  if (r > 0) return EVOLVE_NA;
+  if (r < 0) return ARK_MEM_FAIL;
+  m->tn = st.tn; m->next_h = st.next_h; m->hold = st.hold; m->eta = st.eta; m->etamax = st.etamax;
+  m->ehist[0] = st.ehist[0]; m->ehist[1] = st.ehist[1];
+  m->ynorm_sq_next = st.ynorm_sq;
+  m->nst = st.nst; m->nst_attempts = st.nst_attempts; m->nfe = st.nfe; m->netf = st.netf;
+  m->yn = st.yn; m->yold = st.yold; m->ycur = st.ycur; m->fnew = st.fnew; m->fold = st.fold;
+  m->h = (st.flag < 0 && st.h_failed != 0.0) ? st.h_failed : st.hold;
+  return st.flag;
+}
+
 }  // namespace
 
 extern "C" {
@@ -382,6 +425,12 @@ int crd_ARKodeSetReuseFirstStage(void *mem, int on) {
   ((ArkMem *)mem)->reuse_first = on != 0;
   return ARK_SUCCESS;
 }
+int crd_ARKodeSetResident(void *mem, int on) {
+  if (!mem) return ARK_MEM_NULL;
+  ((ArkMem *)mem)->resident = on != 0;
+  ((ArkMem *)mem)->resident_na = false;
+  return ARK_SUCCESS;
+}
 int crd_ARKodeSetInitStep(void *mem, realtype hin) {
   if (!mem) return ARK_MEM_NULL;
   ((ArkMem *)mem)->hin = hin;
@@ -418,6 +467,30 @@ int ARKode(void *mem, realtype tout, N_Vector yout, realtype *tret, int itask) {
     if (r != 0) return r;
     *tret = tout;
     return ARK_SUCCESS;
+  }
+
+  // device-resident step loop: the vector implementation runs the whole loop below by itself
+  if (m->resident && !m->resident_na && m->fused && m->fused->erk_evolve && m->hfixed == 0.0) {
+    int r = evolve_resident(m, tout, itask);
+    if (r == EVOLVE_NA) m->resident_na = true;
+    else {
+      if (r != ARK_SUCCESS) {
+        if (r == ARK_TOO_MUCH_WORK) std::fprintf(stderr, "crd_ark: at t = %g, mxstep steps taken before reaching tout\n", m->tn);
+        else if (r == ARK_TOO_MUCH_ACC) std::fprintf(stderr, "crd_ark: at t = %g, too much accuracy requested\n", m->tn);
+        else std::fprintf(stderr, "crd_ark: at t = %g and h = %g, step failed with flag %d\n", m->tn, m->h, r);
+        N_VScale(1.0, m->yn, yout); *tret = m->tn;
+        return r;
+      }
+      if (itask == ARK_NORMAL) {
+        int dr = dense_eval(m, tout, yout);
+        if (dr != 0) return dr;
+        *tret = tout;
+      } else {
+        N_VScale(1.0, m->yn, yout);
+        *tret = m->tn;
+      }
+      return ARK_SUCCESS;
+    }
   }
 
   long nstloc = 0;

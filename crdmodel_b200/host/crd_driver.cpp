@@ -12,7 +12,7 @@
 // Ranks are GPUs: `System.gpus = G` (or CRD_GPUS=G) forks G worker processes, one per GPU, each owning a
 // phi slab; neighbours' boundary rows travel through CUDA-IPC peer mappings, norms through shared memory.
 // New optional keys (absent => the reference's behaviour): System.gpus, System.arith (exact|fast),
-// System.fused (1), System.reuseFirstStage (0), Parameters.phiMesh, Parameters.Zs / Ys.
+// System.fused (1), System.reuseFirstStage (0), System.resident (1), Parameters.phiMesh, Parameters.Zs / Ys.
 #include <pthread.h>
 #include <sys/mman.h>
 #include <sys/wait.h>
@@ -122,7 +122,7 @@ struct Config {
   double DIFF, BETA, SURFACE_LENGTH, SURFACE_WIDTH, WAVE_LENGTH, WAVE_WIDTH, T_BOUNDARY, T_FINAL, BETA_MIN = 0, BETA_MAX = 0;
   int WAVE_INSIDE = 0, OUTPUT_TIMESTEP, NX, INCLUDE_ALL_VARS, VARY_BETA, JUST_DIFFUSION = 0, IC_TYPE = 0;
   long ny;
-  int gpus, arith, fused, reuse;
+  int gpus, arith, fused, reuse, resident;
   double Zs = 0, Ys = 0;
   bool have_zs = false;
 };
@@ -173,6 +173,7 @@ Config read_config(const char *path) {
   c.arith = (ar == "fast") ? CRD_ARITH_FAST : CRD_ARITH_EXACT;
   c.fused = pt.get<int>("System.fused", 1);
   c.reuse = pt.get<int>("System.reuseFirstStage", 0);
+  c.resident = pt.get<int>("System.resident", 1);   // 1: the step loop runs as one persistent kernel when it applies
   if (!kFhn) {
     if (pt.has("Parameters.Zs") && pt.has("Parameters.Ys")) {
       c.Zs = pt.get<double>("Parameters.Zs"); c.Ys = pt.get<double>("Parameters.Ys"); c.have_zs = true;
@@ -319,6 +320,7 @@ int run(const Config &c, int rank, int nranks) {
   if (check_flag(&flag, "ARKodeSetMaxNumSteps", 1)) return (1);
   if (c.fused) crd_ARKodeSetFusedOps(arkode_mem, crd_nv_fused_ops());
   crd_ARKodeSetReuseFirstStage(arkode_mem, c.reuse);
+  crd_ARKodeSetResident(arkode_mem, c.resident);
 
   // per-subdomain output files (:375-410)
   const char *stem = file_stem();

@@ -13,6 +13,10 @@
  *               out[0] = sum_global (err_i  * w_i )^2,  w_i  = 1/(rtol |yn_i|   + atol)
  *               out[1] = sum_global (ynew_i * w'_i)^2,  w'_i = 1/(rtol |ynew_i| + atol)
  *               (the error weights are a pure function of the state, so no ewt vector is stored).
+ *   erk_evolve  the whole adaptive step loop (stages, finish, error test, step controller) inside ONE persistent
+ *               cooperative kernel: no launch and no host round trip per step.  For the meshes that live in L2
+ *               (the reference's default 400 x 1600 / 100 x 400 grids) a step is bound by launch latency, not by
+ *               memory: this is what removes it.
  */
 #ifndef CRD_ARK_H
 #define CRD_ARK_H
@@ -24,6 +28,7 @@ extern "C" {
 
 #define CRD_ARK_MAX_LINCOMB 8
 
+struct crd_erk_state;
 typedef struct crd_fused_ops {
   int (*lincomb)(int n, const realtype *c, N_Vector *X, N_Vector z);
   int (*erk_finish)(int s, const realtype *hb, const realtype *hd, N_Vector yn, N_Vector *F,
@@ -31,7 +36,41 @@ typedef struct crd_fused_ops {
   /* optional: ydot = f(t, sum_j c[j] X[j]) in one pass, the stage state never touching memory (n <= 5);
    * same return convention as ARKRhsFn.  Removes the stage-assembly kernels: 480 instead of 592 B/point/step. */
   int (*rhs_lincomb)(realtype t, int n, const realtype *c, N_Vector *X, N_Vector ydot, void *user_data);
+  /* optional: run the adaptive step loop itself on the device (see crd_erk_state).  Returns 0 when it ran
+   * (st->flag then holds what ARKode() would return before its dense-output evaluation), > 0 when it does not
+   * apply to this problem (the integrator continues with its own host-driven loop), < 0 on a launch failure. */
+  int (*erk_evolve)(struct crd_erk_state *st, void *user_data);
 } crd_fused_ops;
+
+/* The integrator's state handed to erk_evolve and taken back from it.  The callee advances (tn, yn, fnew =
+ * f(tn, yn)) by accepted steps of the explicit method (A, b, d = b - b_embedded, c) under the same error test and
+ * PID step controller as the host loop until tn has passed tout (ARK_NORMAL), one step was taken (ARK_ONE_STEP),
+ * max_steps steps were taken, or a step failed.  It owns the role of every vector while it runs and returns them
+ * permuted (the N_Vector handles are swapped, never the data copied): on return yn / fnew are the accepted state
+ * and its derivative, yold / fold those of the step before (dense output), ycur and F[1..s-1] scratch. */
+#define CRD_ERK_MAX_STAGES 8
+typedef struct crd_erk_state {
+  /* method */
+  int s, p;                         /* stages, embedding order */
+  realtype A[CRD_ERK_MAX_STAGES][CRD_ERK_MAX_STAGES], b[CRD_ERK_MAX_STAGES], d[CRD_ERK_MAX_STAGES], c[CRD_ERK_MAX_STAGES];
+  /* tolerances and controller constants (ARKode 1.x defaults: crd_ark.cpp) */
+  realtype rtol, atol;
+  realtype k1, k2, k3, bias, safety, growth, etamxf, etamin, lbound, ubound;
+  int small_nef, maxnef;
+  long int nglobal;                 /* global vector length (WRMS denominator) */
+  /* request */
+  realtype tout;
+  int itask;                        /* ARK_NORMAL | ARK_ONE_STEP */
+  long int max_steps;               /* steps this call may take (<= 0: no limit) */
+  /* evolving state, in/out */
+  realtype tn, next_h, hold, eta, etamax, ehist[2];
+  realtype ynorm_sq;                /* sum_global (yn_i w_i)^2 of the current state, < 0 when unknown */
+  long int nst, nst_attempts, nfe, netf;
+  N_Vector yn, yold, ycur, fnew, fold, F[CRD_ERK_MAX_STAGES];
+  /* out */
+  int flag;                         /* ARK_SUCCESS, ARK_TOO_MUCH_WORK, ARK_TOO_MUCH_ACC, ARK_ERR_FAILURE */
+  realtype h_failed;                /* step size of the failed attempt when flag < 0 */
+} crd_erk_state;
 
 /* Register fused operations (NULL = op-by-op, the SUNDIALS 2.x sequence). */
 int crd_ARKodeSetFusedOps(void *arkode_mem, const crd_fused_ops *ops);
@@ -39,6 +78,10 @@ int crd_ARKodeSetFusedOps(void *arkode_mem, const crd_fused_ops *ops);
  * the end of the previous step.  on=1 reuses it (5 instead of 6 RHS evaluations per step, identical
  * results); on=0 (default) re-evaluates like ARKode 1.x. */
 int crd_ARKodeSetReuseFirstStage(void *arkode_mem, int on);
+/* Device-resident step loop (crd_fused_ops.erk_evolve): on = 1 (default) uses it whenever the registered fused
+ * operations offer it and it applies; on = 0 keeps the host-driven loop (one kernel launch per stage and a host
+ * round trip per step). */
+int crd_ARKodeSetResident(void *arkode_mem, int on);
 /* Initial step size (0 = estimate it, the default). */
 int crd_ARKodeSetInitStep(void *arkode_mem, realtype hin);
 /* Fixed step size (no error test, no adaptivity); 0 switches adaptivity back on. */

@@ -147,6 +147,16 @@ int64_t crd_grid_rhs_count(const crd_grid *g);
 int crd_grid_set_variant(crd_grid *g, int variant);
 /* on (default): ring evaluations compute the interior rows while the boundary rows are exchanged */
 int crd_grid_set_overlap(crd_grid *g, int on);
+/* The adaptive step loop of the explicit integrator as one persistent cooperative kernel (replaces the time loop
+ * inside ARKode(), src/FHNmodel_torus.cpp:423, for meshes that live in L2 such as the shipped 400 x 1600 and
+ * 100 x 400 grids: no kernel launch and no host round trip per step).  user_data is the crd_grid*; this is the
+ * erk_evolve slot of crd_nv_fused_ops() (crd_ark.h).  Returns 0 when it ran, > 0 when it does not apply (several
+ * ranks, a mesh beyond the automatic size limit, a method wider than 5 stages), < 0 on failure. */
+int crd_erk_evolve(struct crd_erk_state *st, void *user_data);
+/* mode: 0 automatic (default: meshes of up to 4 Mi points), 1 whenever it applies, -1 never */
+int crd_grid_set_resident(crd_grid *g, int mode);
+/* how many times the resident loop was launched on this grid */
+int64_t crd_grid_resident_launches(const crd_grid *g);
 
 /* ---- synthetic states and initial conditions --------------------------------------------------- */
 /* 64-bit LCG stream, element e of the global vector uses state e+1 after `seed`;

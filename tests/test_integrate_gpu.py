@@ -59,8 +59,11 @@ def reference_ics(model, nx, ny, beta):
 
 
 @pytest.mark.parametrize("model,nx,ny,touts", [("fhn_torus", 32, 128, [0.5, 1.0, 2.0, 4.0]), ("gb_torus", 24, 96, [0.05, 0.1, 0.2])])
-@pytest.mark.parametrize("fused", [True, False])
-def test_trajectory_parity(crd, ctx, oracle, model, nx, ny, touts, fused):
+@pytest.mark.parametrize("mode", ["resident", "fused", "opbyop"])
+def test_trajectory_parity(crd, ctx, oracle, model, nx, ny, touts, mode):
+    # resident: the whole step loop in one persistent kernel; fused: one launch per stage + fused finish, host loop;
+    # opbyop: the SUNDIALS 2.x vector-op sequence
+    fused, resident = mode != "opbyop", mode == "resident"
     rtol, atol = 1e-5, 1e-10
     beta = 1.25 if model == "fhn_torus" else 0.4
     y0, (s0, s1) = reference_ics(model, nx, ny, beta)
@@ -71,7 +74,7 @@ def test_trajectory_parity(crd, ctx, oracle, model, nx, ny, touts, fused):
     y = grid.new_vector()
     grid.fill_initial_conditions(y, 0.1, 0.5, 1, s0, s1)
     assert y.to_numpy().tobytes() == y0.tobytes()          # device IC generator == the reference's IC loop
-    solver = crd.ARKodeSolver(grid, y, rtol=rtol, atol=atol, fused=fused)
+    solver = crd.ARKodeSolver(grid, y, rtol=rtol, atol=atol, fused=fused, resident=resident)
     for tout, want in zip(touts, cpu):
         flag, t = solver.ARKode(tout)
         assert flag == 0 and t == tout
@@ -80,8 +83,9 @@ def test_trajectory_parity(crd, ctx, oracle, model, nx, ny, touts, fused):
         # the local tolerance of the true solution, so allow a small multiple of it between them
         assert np.all(np.abs(got - want) <= 20 * (rtol * np.abs(want) + atol)), (model, tout, np.abs(got - want).max())
     st = solver.stats()
-    print("\n%s fused=%s: GPU nst=%d nfe=%d netf=%d | CPU nst=%d nfe=%d" % (model, fused, st["nst"], st["nfe"], st["netf"], nst_c, nfe_c))
+    print("\n%s %s: GPU nst=%d nfe=%d netf=%d | CPU nst=%d nfe=%d" % (model, mode, st["nst"], st["nfe"], st["netf"], nst_c, nfe_c))
     assert abs(st["nst"] - nst_c) <= max(2, nst_c // 50)
+    assert grid.resident_launches == (len(touts) if resident else 0)
     solver.free(); grid.close()
 
 
@@ -92,7 +96,7 @@ def test_reuse_first_stage_is_bitwise_neutral(crd, ctx):
     for reuse in (False, True):
         grid = crd.Grid(ctx, crd.make_params("fhn_torus", nx, ny, beta=1.25, vary_beta=0, t_boundary=0.0))
         y = crd.NVector.from_numpy(ctx, y0)
-        s = crd.ARKodeSolver(grid, y, reuse_first_stage=reuse)
+        s = crd.ARKodeSolver(grid, y, reuse_first_stage=reuse, resident=False)
         assert s.ARKode(1.0)[0] == 0
         res.append((y.to_numpy(), s.stats()))
         s.free(); grid.close()
@@ -110,7 +114,7 @@ def test_fused_stage_rhs_does_not_change_the_trajectory(crd, ctx):
         grid = crd.Grid(ctx, crd.make_params("fhn_torus", nx, ny, beta=1.25, vary_beta=0, t_boundary=0.5))
         y = crd.NVector.from_numpy(ctx, y0)
         l0 = ctx.launches
-        s = crd.ARKodeSolver(grid, y, fused=mode)
+        s = crd.ARKodeSolver(grid, y, fused=mode, resident=False)
         assert s.ARKode(1.5)[0] == 0
         res.append((y.to_numpy(), s.stats(), ctx.launches - l0))
         s.free(); grid.close()
