@@ -82,6 +82,7 @@ SIGNATURES = {
     "crd_erk_evolve": (I, [P, P]),
     "crd_grid_set_resident": (I, [P, I]),
     "crd_grid_resident_launches": (C.c_int64, [P]),
+    "crd_grid_resident_cycles": (I, [P, C.POINTER(C.c_int64)]),
     "crd_fill_synthetic": (I, [P, I, C.c_uint64, C.c_int64, C.c_int64, P]),
     "crd_fill_initial_conditions": (I, [P, C.POINTER(IcParams), P]),
     # device N_Vector

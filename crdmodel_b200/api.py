@@ -239,6 +239,12 @@ class Grid:
     def resident_launches(self):
         return lib().crd_grid_resident_launches(self._h)
 
+    def resident_cycles(self):
+        """SM cycles of the last resident launch by part (one CTA's view): phase1, interior, wait, edges, rest, total."""
+        a = (C.c_int64 * 6)()
+        check(lib().crd_grid_resident_cycles(self._h, a), "crd_grid_resident_cycles")
+        return dict(zip(("phase1", "interior", "wait", "edges", "rest", "total"), list(a)))
+
     def set_overlap(self, on):
         check(lib().crd_grid_set_overlap(self._h, 1 if on else 0), "crd_grid_set_overlap")
 

@@ -92,6 +92,7 @@ struct crd_grid {
   // device-resident step loop (crd_resident.cu): -1 off, 0 automatic (meshes that live in L2), 1 always
   int resident = 0;
   int64_t resident_launches = 0;
+  int64_t res_cycles[6] = {};   // last launch, CTA 0: phase 1, interior rows, barrier wait, edge rows, rest, total
   unsigned long long *res_bar = nullptr;
   double *res_partial = nullptr;
   void *res_out_host = nullptr, *res_out_dev = nullptr;

@@ -49,6 +49,7 @@ struct ResOut {            // mapped pinned host memory, written once by CTA 0 w
   int flag, err;
   int yi, fi;              // which of the ping-pong storages hold yn / fnew
   int done;
+  long long cyc[6];        // CTA 0's cycles in: phase 1, interior rows, barrier wait, edge rows, rest, total
 };
 
 struct ResArgs {
@@ -145,129 +146,131 @@ struct StageTab {
   double A[kResStages][kMaxLc];
 };
 
-// what a pass needs besides the combination (32-bit indices: a band is far below 2^31 points)
+// what a pass needs besides the combination (32-bit indices: a band is far below 2^31 points).  Threads are laid out
+// as (row group ty, column tx): a thread keeps its column — metric coefficients and neighbour offsets are per-thread
+// constants — and walks rows ty, ty + G, ...; meshes wider than the CTA loop over columns as well.
 struct PassCfg {
   int nx, rows, n;                     // columns, rows and points of the band
-  int step_i, step_r;                  // NT % nx, NT / nx: how (row, column) advance when the point index advances by NT
+  int ncol, G, tx, ty;                 // threads along theta, row groups, this thread's place (ty >= G: idle)
   const double2 *cth;                  // [nx] metric coefficients, shared-memory copy
   const double *brow;                  // [rows] beta row values of the band, shared-memory copy
   int react, freeze_south, freeze_north;
 };
 
 // phase 1: the stage state of every point of the band -> tile; its first / last row's u -> exchange buffer
-template <int NT, int N>
+template <int N, int U>   // U: rows in flight per thread
 __device__ __forceinline__ void phase1_n(const Comb &cb, const PassCfg &c, double2 *tile, double *xch_mine) {
-  constexpr int U = 4;
-  const int n = c.n, nx = c.nx;
-  for (int base = threadIdx.x; base < n; base += NT * U) {
-    double2 v[U][N];
+  if (c.ty >= c.G) return;
+  const int nx = c.nx, rows = c.rows, stride = c.G * nx;
+  for (int i = c.tx; i < nx; i += c.ncol) {
+    for (int r0 = c.ty; r0 < rows; r0 += c.G * U) {
+      const int p0 = r0 * nx + i;
+      double2 v[U][N];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = (base + u * NT < n) ? base + u * NT : base;
+      for (int u = 0; u < U; ++u) {
+        const int p = (r0 + u * c.G < rows) ? p0 + u * stride : p0;
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[u][j] = cb.x[j][p];
-    }
+        for (int j = 0; j < N; ++j) v[u][j] = cb.x[j][p];
+      }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = base + u * NT;
-      // sum_j c_j x_j in the operation order of state2<true> / lincomb_kernel
-      double2 s = make_double2(cb.c[0] * v[u][0].x, cb.c[0] * v[u][0].y);
+      for (int u = 0; u < U; ++u) {
+        const int r = r0 + u * c.G;
+        // sum_j c_j x_j in the operation order of state2<true> / lincomb_kernel
+        double2 s = make_double2(cb.c[0] * v[u][0].x, cb.c[0] * v[u][0].y);
 #pragma unroll
-      for (int j = 1; j < N; ++j) { s.x = fma(cb.c[j], v[u][j].x, s.x); s.y = fma(cb.c[j], v[u][j].y, s.y); }
-      if (p < n) {
-        tile[p] = s;
-        if (p < nx) xch_mine[p] = s.x;
-        if (p >= n - nx) xch_mine[nx + (p - (n - nx))] = s.x;
+        for (int j = 1; j < N; ++j) { s.x = fma(cb.c[j], v[u][j].x, s.x); s.y = fma(cb.c[j], v[u][j].y, s.y); }
+        if (r < rows) {
+          tile[p0 + u * stride] = s;
+          if (r == 0) xch_mine[i] = s.x;
+          if (r == rows - 1) xch_mine[nx + i] = s.x;
+        }
       }
     }
   }
 }
-template <int NT>
+template <int U>
 __device__ __forceinline__ void phase1(const Comb &cb, const PassCfg &c, double2 *tile, double *xch_mine) {
   switch (cb.n) {
-    case 1: phase1_n<NT, 1>(cb, c, tile, xch_mine); break;
-    case 2: phase1_n<NT, 2>(cb, c, tile, xch_mine); break;
-    case 3: phase1_n<NT, 3>(cb, c, tile, xch_mine); break;
-    case 4: phase1_n<NT, 4>(cb, c, tile, xch_mine); break;
-    default: phase1_n<NT, 5>(cb, c, tile, xch_mine); break;
+    case 1: phase1_n<1, U>(cb, c, tile, xch_mine); break;
+    case 2: phase1_n<2, U>(cb, c, tile, xch_mine); break;
+    case 3: phase1_n<3, U>(cb, c, tile, xch_mine); break;
+    case 4: phase1_n<4, (U > 2 ? 2 : U)>(cb, c, tile, xch_mine); break;    // wide combinations: fewer rows in flight (registers)
+    default: phase1_n<5, (U > 2 ? 2 : U)>(cb, c, tile, xch_mine); break;
   }
 }
 
-// one point of phase 2: stencil + reaction from the tile; writes F to `out`, or (last stage, fin != nullptr) the step finish
-template <int MODEL, bool EXACT>
-__device__ __forceinline__ void point2(const PassCfg &c, const RhsConst &k, const double2 *tile, const double *xs, const double *xn,
-                                       double2 *out, const ResFinish *fin, int p, int r, int i, double &e2, double &y2) {
-  const int nx = c.nx;
-  const int row = p - i;
-  const double2 cc = tile[p];
-  const double uW = tile[row + (i == 0 ? nx - 1 : i - 1)].x;
-  const double uE = tile[row + (i == nx - 1 ? 0 : i + 1)].x;
-  const double uS = (r == 0) ? __ldcg(xs + i) : tile[p - nx].x;
-  const double uN = (r == c.rows - 1) ? __ldcg(xn + i) : tile[p + nx].x;
-  double t1 = 0.0, t3 = 0.0;
-  if (is_torus(MODEL)) {
-    const double2 tc = c.cth[i];
-    t1 = tc.x; t3 = tc.y;
-  }
-  double du = EXACT ? stencil_exact<MODEL>(k, t1, t3, cc.x, uW, uE, uS, uN) : stencil_fast<MODEL>(k, t1, t3, cc.x, uW, uE, uS, uN);
-  double dv = 0.0;
-  if (c.react) {
-    const bool frozen = (c.freeze_north && r == c.rows - 1) || (c.freeze_south && r == 0);
-    if (frozen) { du = 0.0; dv = 0.0; }
-    else react<MODEL, EXACT>(k, c.brow[r], cc.x, cc.y, du, dv);
-  }
-  if (fin == nullptr) {
-    out[p] = make_double2(du, dv);
-  } else {
-    // last stage: the step's solution, error estimate and the two weighted square sums (crd_fused.cuh)
-    const double2 y0 = fin->yn[p];
-    double sx = y0.x, sy = y0.y, ex = 0.0, ey = 0.0;
+// weighted squares of the finish with the reciprocal of the weight's denominator from rcp.approx + 3 Newton steps
+// (~1 ulp, no IEEE slow path and so no branch: the rows in flight interleave).  The sums only feed the error norm,
+// whose bits already depend on the summation order; ynew itself is formed exactly like erk_finish_kernel forms it.
+__device__ __forceinline__ void finish_tail_rcp(double rtol, double atol, double yn, double s, double err, double &e2, double &y2) {
+  const double pe = err * rcp_fast(fma(rtol, fabs(yn), atol)), py = s * rcp_fast(fma(rtol, fabs(s), atol));
+  e2 += pe * pe;
+  y2 += py * py;
+}
+
+// phase 2 over rows r = r_first + k * r_step, k = 0 .. nr-1, of the band (row k goes to row group k % G): stencil +
+// reaction with every neighbour a shared-memory read; the rows just outside the band are the neighbours' exchange
+// rows.  Writes F to `out`, or (FIN: last stage) finishes the step with the last stage's derivative still in registers
+// (crd_fused.cuh arithmetic).
+template <int MODEL, bool EXACT, bool FIN>
+__device__ __forceinline__ void phase2_rows(const PassCfg &c, const RhsConst &k_in, const double2 *tile, const double *xs, const double *xn,
+                                            double2 *out, const ResFinish *fin, int r_first, int r_step, int nr, double &e2, double &y2) {
+  if (c.ty >= c.G) return;
+  const int nx = c.nx, rows = c.rows;
+  const int S = FIN ? fin->s : 0;
+  const RhsConst k = k_in;   // registers: a generic store may alias shared memory, which would force a reload per row
+  for (int i = c.tx; i < nx; i += c.ncol) {
+    const int iw = (i == 0) ? nx - 1 : i - 1, ie = (i == nx - 1) ? 0 : i + 1;   // theta wraps
+    double t1 = 0.0, t3 = 0.0;
+    if (is_torus(MODEL)) {
+      const double2 tc = c.cth[i];
+      t1 = tc.x; t3 = tc.y;
+    }
+#pragma unroll 1
+    for (int q = c.ty; q < nr; q += c.G) {
+      const int r = r_first + q * r_step;
+      const int row = r * nx, p = row + i;
+      const double2 cc = tile[p];
+      const double uW = tile[row + iw].x, uE = tile[row + ie].x;
+      const double uS = (r == 0) ? __ldcg(xs + i) : tile[p - nx].x;
+      const double uN = (r == rows - 1) ? __ldcg(xn + i) : tile[p + nx].x;
+      double du = EXACT ? stencil_exact<MODEL>(k, t1, t3, cc.x, uW, uE, uS, uN) : stencil_fast<MODEL>(k, t1, t3, cc.x, uW, uE, uS, uN);
+      double dv = 0.0;
+      if (c.react) {
+        const bool frozen = (c.freeze_north && r == rows - 1) || (c.freeze_south && r == 0);
+        if (frozen) { du = 0.0; dv = 0.0; }
+        else react<MODEL, EXACT>(k, c.brow[r], cc.x, cc.y, du, dv);
+      }
+      if (!FIN) {
+        out[p] = make_double2(du, dv);
+      } else {
+        const double2 y0 = fin->yn[p];
+        double sx = y0.x, sy = y0.y, ex = 0.0, ey = 0.0;
 #pragma unroll
-    for (int j = 0; j < kResStages; ++j) {
-      if (j < fin->s) {
-        const double2 f = (j == fin->s - 1) ? make_double2(du, dv) : fin->F[j][p];
-        sx = fma(fin->hb[j], f.x, sx); ex = fma(fin->hd[j], f.x, ex);
-        sy = fma(fin->hb[j], f.y, sy); ey = fma(fin->hd[j], f.y, ey);
+        for (int j = 0; j < kResStages; ++j) {
+          if (j < S) {
+            const double2 fj = (j == S - 1) ? make_double2(du, dv) : fin->F[j][p];
+            sx = fma(fin->hb[j], fj.x, sx); ex = fma(fin->hd[j], fj.x, ex);
+            sy = fma(fin->hb[j], fj.y, sy); ey = fma(fin->hd[j], fj.y, ey);
+          }
+        }
+        fin->ynew[p] = make_double2(sx, sy);
+        finish_tail_rcp(fin->rtol, fin->atol, y0.x, sx, ex, e2, y2);
+        finish_tail_rcp(fin->rtol, fin->atol, y0.y, sy, ey, e2, y2);
       }
     }
-    fin->ynew[p] = make_double2(sx, sy);
-    finish_tail(fin->rtol, fin->atol, y0.x, sx, ex, e2, y2);
-    finish_tail(fin->rtol, fin->atol, y0.y, sy, ey, e2, y2);
   }
 }
 
-// phase 2 over the band's rows [r_lo, r_hi): neighbours are shared-memory reads, the rows just outside the band the
-// neighbours' exchange rows.  Interior rows (1 .. rows-2) need nothing from other SMs and run before the barrier wait.
-template <int MODEL, bool EXACT, int NT>
-__device__ __forceinline__ void phase2_rows(const PassCfg &c, const RhsConst &k, const double2 *tile, const double *xs, const double *xn,
-                                            double2 *out, const ResFinish *fin, int r_lo, int r_hi, double &e2, double &y2) {
-  const int nx = c.nx;
-  const int end = r_hi * nx;
-  int r = r_lo + (int)threadIdx.x / nx, i = (int)threadIdx.x % nx;
-#pragma unroll 2
-  for (int p = r_lo * nx + (int)threadIdx.x; p < end; p += NT) {
-    point2<MODEL, EXACT>(c, k, tile, xs, xn, out, fin, p, r, i, e2, y2);
-    i += c.step_i; r += c.step_r;
-    if (i >= nx) { i -= nx; ++r; }
-  }
-}
-// ... and over the band's first and last row
-template <int MODEL, bool EXACT, int NT>
-__device__ __forceinline__ void phase2_edges(const PassCfg &c, const RhsConst &k, const double2 *tile, const double *xs, const double *xn,
-                                             double2 *out, const ResFinish *fin, double &e2, double &y2) {
-  const int nx = c.nx, ne = (c.rows > 1) ? 2 * nx : nx;
-  for (int e = threadIdx.x; e < ne; e += NT) {
-    const bool north = e >= nx;
-    const int i = north ? e - nx : e, r = north ? c.rows - 1 : 0;
-    point2<MODEL, EXACT>(c, k, tile, xs, xn, out, fin, r * nx + i, r, i, e2, y2);
-  }
-}
-
-// PID controller + bounds: the arithmetic of adapt_eta() in crd_ark.cpp
-__device__ double res_adapt_eta(const ResArgs &P, double hcur, double dsm, double eh0, double eh1, double etamax) {
+// PID controller + bounds: the arithmetic of adapt_eta() in crd_ark.cpp.  Called by a whole warp: the three pow() run
+// on lanes 0..2 at the same time (one pow latency instead of three); every lane returns the same value.
+__device__ double res_adapt_eta(const ResArgs &P, double hcur, double dsm, double eh0, double eh1, double etamax, int lane) {
   const double k = (double)P.p;
-  const double e1 = fmax(P.bias * dsm, 1.0e-10), e2 = fmax(eh0, 1.0e-10), e3 = fmax(eh1, 1.0e-10);
-  double h_acc = hcur * pow(e1, -P.k1 / k) * pow(e2, P.k2 / k) * pow(e3, -P.k3 / k);
+  const double base = lane == 0 ? fmax(P.bias * dsm, 1.0e-10) : lane == 1 ? fmax(eh0, 1.0e-10) : fmax(eh1, 1.0e-10);
+  const double expo = lane == 0 ? -P.k1 / k : lane == 1 ? P.k2 / k : -P.k3 / k;
+  const double pw = pow(base, expo);
+  const double p1 = __shfl_sync(0xffffffffu, pw, 0), p2 = __shfl_sync(0xffffffffu, pw, 1), p3 = __shfl_sync(0xffffffffu, pw, 2);
+  double h_acc = hcur * p1 * p2 * p3;
   const double int_dir = hcur / fabs(hcur);
   h_acc *= P.safety;
   h_acc = int_dir * fmin(fabs(h_acc), fabs(etamax * hcur));
@@ -300,8 +303,10 @@ __global__ void __launch_bounds__(NT, 1) erk_resident_kernel(const ResArgs P) {
 
   PassCfg cfg;
   cfg.nx = (int)nx; cfg.rows = (int)(j1 - j0); cfg.n = cfg.rows * cfg.nx;
-  cfg.step_i = NT % cfg.nx; cfg.step_r = NT / cfg.nx;
+  cfg.ncol = cfg.nx < NT ? cfg.nx : NT; cfg.G = NT / cfg.ncol;
+  cfg.ty = (int)threadIdx.x / cfg.ncol; cfg.tx = (int)threadIdx.x - cfg.ty * cfg.ncol;
   cfg.cth = cth_s; cfg.brow = brow_s; cfg.react = P.react; cfg.freeze_south = 0; cfg.freeze_north = 0;
+  const int n_edge = cfg.rows > 1 ? 2 : 1;   // the band's first and last row: need the neighbours' exchange rows
 
   // exchange rows: [parity][band][first | last][nx]
   auto xch_mine = [&](unsigned par) { return P.xch + ((size_t)(par & 1u) * nb + b) * 2 * nx; };
@@ -340,12 +345,12 @@ __global__ void __launch_bounds__(NT, 1) erk_resident_kernel(const ResArgs P) {
     L.h = L.next_h;
   };
   // phase 1 of a pass, then this CTA's arrival at the pass's barrier
-  auto stage_tile = [&](const Comb &cb) {
-    phase1<NT>(cb, cfg, tile, xch_mine(L.pass));
-    __syncthreads();                       // the tile and the CTA's exchange rows (and error partials) are written
-    if (threadIdx.x == 0) grid_arrive(P.bar, bar_target);
+  // where the time goes, as seen by thread 0 (reported for CTA 0): cycles since the previous tick are booked on `k`
+  long long cyc[5] = {0, 0, 0, 0, 0}, t_last = clock64();
+  const long long t_begin = t_last;
+  auto tick = [&](int k) {
+    if (threadIdx.x == 0) { const long long now = clock64(); cyc[k] += now - t_last; t_last = now; }
   };
-
   if (threadIdx.x == 0) {
     L.tn = P.tn; L.next_h = P.next_h; L.h = P.next_h; L.hold = P.hold; L.eta = P.eta; L.etamax = P.etamax;
     L.eh0 = P.eh0; L.eh1 = P.eh1; L.ynorm_sq = P.ynorm_sq; L.h_failed = 0.0;
@@ -380,119 +385,126 @@ __global__ void __launch_bounds__(NT, 1) erk_resident_kernel(const ResArgs P) {
   }
   __syncthreads();
 
+  // ---- the passes: stage 1 .. s-1 of an attempt, then fnew = f(tn + h, ynew) ------------------------------------------
+  // One code path for every pass (a single inlined copy of each phase keeps the kernel inside the instruction cache):
+  //   phase 1 of the pass's state, arrive | interior rows | wait | [after the last stage: error test] | edge rows
   bool alive = true;
-  if (L.status != 2) {
-    stage_tile(stage_comb(1, L.h));
-    for (;;) {   // steps
-      for (;;) {   // attempts
-        double e2 = 0.0, y2 = 0.0;
-        for (int is = 1; is < P.s; ++is) {
-          // here: the tile holds the stage-is state, this CTA has arrived at the pass's barrier
-          const bool last = (is == P.s - 1);
-          const double h = L.h;
-          if (last && threadIdx.x == 0) {
-            sf.yn = S[ST_Y0 + L.yi]; sf.ynew = S[ST_Y0 + (L.yi ^ 1)];
-            for (int j = 0; j < P.s; ++j) {
-              sf.F[j] = (j == 0) ? S[ST_FA + L.fi] : S[ST_F1 + (j < P.s - 1 ? j : 1) - 1];
-              sf.hb[j] = __dmul_rn(h, P.b[j]); sf.hd[j] = __dmul_rn(h, P.d[j]);
-            }
-          }
-          if (last) __syncthreads();
-          set_freeze(__dadd_rn(L.tn, __dmul_rn(P.c[is], h)));
-          double2 *out = last ? nullptr : S[ST_F1 + is - 1];
-          const ResFinish *fin = last ? &sf : nullptr;
-          const double *xs = halo_south(L.pass), *xn = halo_north(L.pass);
-          // interior rows first: they need nothing from the neighbours, so the barrier's latency hides behind them
-          phase2_rows<MODEL, EXACT, NT>(cfg, sk, tile, xs, xn, out, fin, 1, cfg.rows - 1, e2, y2);
-          if (!grid_wait(P.bar, bar_target, &s_ok)) { alive = false; break; }
-          phase2_edges<MODEL, EXACT, NT>(cfg, sk, tile, xs, xn, out, fin, e2, y2);
-          if (last) {
-            // CTA partial sums, fixed order: shuffle tree, then the warps in order
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { e2 += __shfl_down_sync(0xffffffffu, e2, o); y2 += __shfl_down_sync(0xffffffffu, y2, o); }
-            if (lane == 0) { s_red[0][warp] = e2; s_red[1][warp] = y2; }
-          }
-          __syncthreads();          // every read of the tile is done; the band's F_is (or ynew) is complete
-          if (threadIdx.x == 0) {
-            if (last) {
-              double se = s_red[0][0], sy = s_red[1][0];
-              for (int w = 1; w < NW; ++w) { se += s_red[0][w]; sy += s_red[1][w]; }
-              P.partial[b] = se;
-              P.partial[nb + b] = sy;
-            }
-            if (is == 1) L.attempts++;
-            L.nfe++;
-            L.pass++;
-          }
-          __syncthreads();
-          // next pass's state: the following stage, or (speculating that the step is accepted) ynew for fnew = f(tn + h, ynew)
-          if (last) stage_tile(identity_comb(ST_Y0 + (L.yi ^ 1)));
-          else stage_tile(stage_comb(is + 1, h));
-        }
-        if (!alive) break;
+  int is = 1;                       // the pass: stage `is` for is < s, is == s: fnew of the state the last stage produced
+  double e2 = 0.0, y2 = 0.0;
+  while (L.status != 2) {
+    const int s_ = P.s;
+    const bool fnew_pass = (is == s_), last = (is == s_ - 1);
+    const double h = L.h;
+    tick(4);
+    // phase 1: this pass's state into the tile, the band's edge rows into the exchange buffer; then arrive
+    phase1<4>(fnew_pass ? identity_comb(ST_Y0 + (L.yi ^ 1)) : stage_comb(is, h), cfg, tile, xch_mine(L.pass));
+    if (last && threadIdx.x == 0) {
+      sf.yn = S[ST_Y0 + L.yi]; sf.ynew = S[ST_Y0 + (L.yi ^ 1)];
+      for (int j = 0; j < s_; ++j) {
+        sf.F[j] = (j == 0) ? S[ST_FA + L.fi] : S[ST_F1 + (j < s_ - 1 ? j : 1) - 1];
+        sf.hb[j] = __dmul_rn(h, P.b[j]); sf.hd[j] = __dmul_rn(h, P.d[j]);
+      }
+    }
+    __syncthreads();                       // the tile, the CTA's exchange rows and (after a last stage) its error partials are written
+    if (threadIdx.x == 0) grid_arrive(P.bar, bar_target);
+    tick(0);
+    const double *xs = halo_south(L.pass), *xn = halo_north(L.pass);
+    double2 *out = fnew_pass ? S[ST_FA + (L.fi ^ 1)] : last ? nullptr : S[ST_F1 + is - 1];
+    if (!fnew_pass) set_freeze(__dadd_rn(L.tn, __dmul_rn(P.c[is], h)));
+    bool rejected = false;
+    for (int part = 0; part < 2; ++part) {
+      int r_first, r_step, nr;
+      if (part == 0) {
+        // interior rows need nothing from the neighbours: the barrier's latency hides behind them (the fnew pass has
+        // to know the verdict first)
+        r_first = 1; r_step = 1; nr = fnew_pass ? 0 : cfg.rows - 2;
+      } else {
         if (!grid_wait(P.bar, bar_target, &s_ok)) { alive = false; break; }
-        // ---- error norm: every CTA adds all partials in the same order, then the same test and controller ----
-        if (warp == 0) {
-          double se = 0.0, sy = 0.0;
-          for (int q = lane; q < nb; q += 32) { se += __ldcg(P.partial + q); sy += __ldcg(P.partial + nb + q); }
+        tick(2);
+        if (fnew_pass) {
+          // ---- error norm: every CTA adds all partials in the same order, then the same test and controller ----
+          if (warp == 0) {
+            double se = 0.0, sy = 0.0;
+            for (int q = lane; q < nb; q += 32) { se += __ldcg(P.partial + q); sy += __ldcg(P.partial + nb + q); }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) { se += __shfl_down_sync(0xffffffffu, se, o); sy += __shfl_down_sync(0xffffffffu, sy, o); }
-          if (lane == 0) {
+            for (int o = 16; o > 0; o >>= 1) { se += __shfl_down_sync(0xffffffffu, se, o); sy += __shfl_down_sync(0xffffffffu, sy, o); }
+            se = __shfl_sync(0xffffffffu, se, 0);
             const double dsm = sqrt(se / P.nglobal);
-            L.eta = res_adapt_eta(P, L.h, dsm, L.eh0, L.eh1, L.etamax);
-            if (dsm <= 1.0) {
-              L.eh1 = L.eh0; L.eh0 = dsm * P.bias;
-              L.ynorm_sq = sy;
-              L.status = 1;
-              // complete the step: yn <- ynew (ping-pong); fnew = f(tn, yn) goes into the other F storage
-              L.yi ^= 1;
-              L.hold = L.h;
-              L.tn += L.h;
-              L.nst++;
-              L.etamax = P.growth;
-              L.next_h = L.h * L.eta;
-              L.stop = (P.itask == ARK_ONE_STEP) || ((L.tn - P.tout) * L.h >= 0.0);
-            } else {
-              L.nef++; L.netf++;
-              L.etamax = 1.0;
-              if (L.nef == P.maxnef) { L.flag = ARK_ERR_FAILURE; L.h_failed = L.h; L.status = 2; }
-              else {
-                double eta = fmin(res_adapt_eta(P, L.h, dsm, L.eh0, L.eh1, L.etamax), 1.0);
-                if (L.nef >= P.small_nef) eta = fmin(eta, P.etamxf);
-                L.eta = eta;
-                L.h *= eta;
-                if (fabs(L.h) <= 0.0 || L.tn + L.h == L.tn) { L.flag = ARK_ERR_FAILURE; L.h_failed = L.h; L.status = 2; }
+            const double eta_a = res_adapt_eta(P, L.h, dsm, L.eh0, L.eh1, L.etamax, lane);
+            const double eta_r = res_adapt_eta(P, L.h, dsm, L.eh0, L.eh1, 1.0, lane);   // after a failure etamax is 1
+            if (lane == 0) {
+              L.eta = eta_a;
+              if (dsm <= 1.0) {
+                L.eh1 = L.eh0; L.eh0 = dsm * P.bias;
+                L.ynorm_sq = sy;
+                L.status = 1;
+                // complete the step: yn <- ynew (ping-pong); fnew goes into the other F storage
+                L.yi ^= 1;
+                L.hold = L.h;
+                L.tn += L.h;
+                L.nst++;
+                L.etamax = P.growth;
+                L.next_h = L.h * L.eta;
+                L.stop = (P.itask == ARK_ONE_STEP) || ((L.tn - P.tout) * L.h >= 0.0);
+              } else {
+                L.status = 0;
+                L.nef++; L.netf++;
+                L.etamax = 1.0;
+                if (L.nef == P.maxnef) { L.flag = ARK_ERR_FAILURE; L.h_failed = L.h; L.status = 2; }
+                else {
+                  double eta = fmin(eta_r, 1.0);
+                  if (L.nef >= P.small_nef) eta = fmin(eta, P.etamxf);
+                  L.eta = eta;
+                  L.h *= eta;
+                  if (fabs(L.h) <= 0.0 || L.tn + L.h == L.tn) { L.flag = ARK_ERR_FAILURE; L.h_failed = L.h; L.status = 2; }
+                }
               }
             }
           }
+          __syncthreads();
+          if (L.status != 1) { rejected = true; break; }
+          set_freeze(L.tn);
+          r_first = 0; r_step = 1; nr = cfg.rows;
+        } else {
+          r_first = 0; r_step = cfg.rows - 1; nr = n_edge;
         }
-        __syncthreads();
-        if (L.status != 0) break;
-        // rejected: the tile holds ynew; replace it by the retry's stage-1 state with the smaller step (same parity)
-        stage_tile(stage_comb(1, L.h));
       }
-      if (!alive || L.status == 2) break;
-
-      // ---- fnew = f(tn, yn) of the accepted state: the tile already holds it, the barrier has been passed ----
-      {
-        double e2 = 0.0, y2 = 0.0;
-        set_freeze(L.tn);
-        double2 *out = S[ST_FA + (L.fi ^ 1)];
-        const double *xs = halo_south(L.pass), *xn = halo_north(L.pass);
-        phase2_rows<MODEL, EXACT, NT>(cfg, sk, tile, xs, xn, out, nullptr, 1, cfg.rows - 1, e2, y2);
-        phase2_edges<MODEL, EXACT, NT>(cfg, sk, tile, xs, xn, out, nullptr, e2, y2);
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        L.fi ^= 1;
-        L.nfe++;
-        L.pass++;
-        if (!L.stop) step_top();
-      }
-      __syncthreads();
-      if (L.stop || L.status == 2) break;
-      stage_tile(stage_comb(1, L.h));   // stage 1 of the next step
+      if (last) phase2_rows<MODEL, EXACT, true>(cfg, sk, tile, xs, xn, out, &sf, r_first, r_step, nr, e2, y2);
+      else phase2_rows<MODEL, EXACT, false>(cfg, sk, tile, xs, xn, out, nullptr, r_first, r_step, nr, e2, y2);
+      tick(part == 0 ? 1 : 3);
     }
+    if (!alive) break;
+    if (rejected) {
+      // the tile holds a ynew nobody wants: retry from stage 1 with the smaller step (or stop: status 2)
+      is = 1;
+      continue;
+    }
+    if (last) {
+      // CTA partial sums, fixed order: shuffle tree, then the warps in order
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { e2 += __shfl_down_sync(0xffffffffu, e2, o); y2 += __shfl_down_sync(0xffffffffu, y2, o); }
+      if (lane == 0) { s_red[0][warp] = e2; s_red[1][warp] = y2; }
+      e2 = 0.0; y2 = 0.0;
+    }
+    __syncthreads();          // every read of the tile is done; the band's F_is / ynew / fnew is complete
+    if (threadIdx.x == 0) {
+      if (last) {
+        double se = s_red[0][0], sy = s_red[1][0];
+        for (int w = 1; w < NW; ++w) { se += s_red[0][w]; sy += s_red[1][w]; }
+        P.partial[b] = se;
+        P.partial[nb + b] = sy;
+      }
+      if (is == 1) L.attempts++;
+      L.nfe++;
+      L.pass++;
+      if (fnew_pass) {
+        L.fi ^= 1;
+        if (L.stop) L.status = 2;
+        else step_top();
+      }
+    }
+    __syncthreads();
+    is = fnew_pass ? 1 : is + 1;
   }
 
   // ---- back to the global homes: yn, fnew and (after at least one step) the previous step's state for dense output ----
@@ -514,6 +526,9 @@ __global__ void __launch_bounds__(NT, 1) erk_resident_kernel(const ResArgs P) {
     o->nst = L.nst; o->attempts = L.attempts; o->nfe = L.nfe; o->netf = L.netf;
     o->flag = L.flag; o->err = alive ? 0 : 1;
     o->yi = L.yi; o->fi = L.fi;
+    tick(4);
+    for (int q = 0; q < 5; ++q) o->cyc[q] = cyc[q];
+    o->cyc[5] = clock64() - t_begin;
     __threadfence_system();
     o->done = 1;
     __threadfence_system();
@@ -532,7 +547,8 @@ ResKernel *res_kernel_entry() {
   return &k;
 }
 
-// 512 threads per CTA: 128 registers per thread (1024 x 64 spills the 4-points-in-flight loads and measured no faster)
+// 512 threads per CTA, 128 registers per thread.  Measured on the 400 x 1600 mesh: 1024 threads x 64 registers shorten
+// the stencil phase by 20 % but spill, lengthen every other phase and lose 5 % per step.
 template <int MODEL, bool EXACT>
 ResKernel *res_pick_nt(int) {
   return res_kernel_entry<MODEL, EXACT, 512>();
@@ -563,6 +579,12 @@ int crd_grid_set_resident(crd_grid *g, int mode) {
 }
 
 int64_t crd_grid_resident_launches(const crd_grid *g) { return g ? g->resident_launches : 0; }
+
+int crd_grid_resident_cycles(const crd_grid *g, int64_t out[6]) {
+  if (!g || !out) return -1;
+  for (int q = 0; q < 6; ++q) out[q] = g->res_cycles[q];
+  return 0;
+}
 
 int crd_erk_evolve(struct crd_erk_state *st, void *user_data) {
   crd_grid *g = (crd_grid *)user_data;
@@ -667,6 +689,7 @@ int crd_erk_evolve(struct crd_erk_state *st, void *user_data) {
   st->ehist[0] = out->eh0; st->ehist[1] = out->eh1; st->ynorm_sq = out->ynorm_sq; st->h_failed = out->h_failed;
   st->nst += (long)out->nst; st->nst_attempts += (long)out->attempts; st->nfe += (long)out->nfe; st->netf += (long)out->netf;
   g->rhs_count += out->nfe;
+  for (int q = 0; q < 6; ++q) g->res_cycles[q] = out->cyc[q];
   if (out->nst > 0) {
     // the loop ping-pongs between (yn, ycur) and (fnew, fold); the caller's yold array is free from the first accepted step on
     st->yn = in[storage_home(ST_Y0 + out->yi)]; st->yold = in[storage_home(ST_Y0 + (out->yi ^ 1))]; st->ycur = in[R_YOLD];

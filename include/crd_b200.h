@@ -157,6 +157,9 @@ int crd_erk_evolve(struct crd_erk_state *st, void *user_data);
 int crd_grid_set_resident(crd_grid *g, int mode);
 /* how many times the resident loop was launched on this grid */
 int64_t crd_grid_resident_launches(const crd_grid *g);
+/* where the last resident launch spent its SM cycles, as seen by one CTA: phase 1 (stage state), interior rows,
+ * grid-barrier wait, edge rows, everything else, total */
+int crd_grid_resident_cycles(const crd_grid *g, int64_t out[6]);
 
 /* ---- synthetic states and initial conditions --------------------------------------------------- */
 /* 64-bit LCG stream, element e of the global vector uses state e+1 after `seed`;
