@@ -140,3 +140,108 @@ def test_reference_main_runs_end_to_end(oracle, tmp_path):
     v = np.loadtxt(tmp_path / "FHNmodel_torus_v.000.txt")
     assert u.shape == (4, 12 * 48) and v.shape == (4, 12 * 48)     # ICs + 3 outputs
     assert np.isfinite(u).all() and set(np.unique(u[0])) == {-1.25, 0.75}
+
+
+# ---- the erk_evolve hook (crd_ark.h): the vector implementation may run the whole step loop itself ----------------
+S_MAX = 8
+
+
+class ErkState(C.Structure):
+    """crd_erk_state of include/crd_ark.h"""
+    _fields_ = [("s", C.c_int), ("p", C.c_int),
+                ("A", D_ * S_MAX * S_MAX), ("b", D_ * S_MAX), ("d", D_ * S_MAX), ("c", D_ * S_MAX),
+                ("rtol", D_), ("atol", D_),
+                ("k1", D_), ("k2", D_), ("k3", D_), ("bias", D_), ("safety", D_), ("growth", D_), ("etamxf", D_), ("etamin", D_),
+                ("lbound", D_), ("ubound", D_),
+                ("small_nef", C.c_int), ("maxnef", C.c_int), ("nglobal", L_),
+                ("tout", D_), ("itask", C.c_int), ("max_steps", L_),
+                ("tn", D_), ("next_h", D_), ("hold", D_), ("eta", D_), ("etamax", D_), ("ehist", D_ * 2), ("ynorm_sq", D_),
+                ("nst", L_), ("nst_attempts", L_), ("nfe", L_), ("netf", L_),
+                ("yn", P_), ("yold", P_), ("ycur", P_), ("fnew", P_), ("fold", P_), ("F", P_ * S_MAX),
+                ("flag", C.c_int), ("h_failed", D_)]
+
+
+EVOLVE = C.CFUNCTYPE(C.c_int, C.POINTER(ErkState), P_)
+
+
+class FusedOps(C.Structure):
+    _fields_ = [("lincomb", P_), ("erk_finish", P_), ("rhs_lincomb", P_), ("erk_evolve", EVOLVE)]
+
+
+def integrate_with_evolve(K, f, y0, touts, evolve, mxsteps=200000):
+    K.crd_ARKodeSetFusedOps.argtypes = [P_, C.POINTER(FusedOps)]
+    ops = FusedOps(None, None, None, EVOLVE(evolve))
+    y = np.array(y0, dtype=np.float64)
+    Y = K.N_VMake_Parallel(0, y.size, y.size, y.ctypes.data)
+    mem = P_(K.ARKodeCreate())
+    assert K.ARKodeInit(mem, C.cast(f, P_), None, 0.0, Y) == 0
+    assert K.ARKodeSStolerances(mem, 1e-8, 1e-12) == 0
+    K.ARKodeSetMaxNumSteps(mem, mxsteps)
+    assert K.crd_ARKodeSetFusedOps(mem, C.byref(ops)) == 0
+    outs, flags, ts = [], [], []
+    t = D_()
+    for tout in touts:
+        flags.append(K.ARKode(mem, tout, Y, C.byref(t), 1))
+        outs.append(y.copy()); ts.append(t.value)
+    nst, nfe, nfi = L_(), L_(), L_()
+    K.ARKodeGetNumSteps(mem, C.byref(nst)); K.ARKodeGetNumRhsEvals(mem, C.byref(nfe), C.byref(nfi))
+    K.ARKodeFree(C.byref(mem))
+    return outs, flags, ts, dict(nst=nst.value, nfe=nfe.value)
+
+
+def test_evolve_hook_not_applicable_falls_back_to_the_host_loop(K):
+    f = make_rhs(K, lambda t, y: np.array([y[1], -y[0]]))
+    calls = []
+    def evolve(st, user):
+        calls.append(st.contents.tn)
+        return 1          # "does not apply": the integrator must carry on by itself and stop asking
+    touts = [0.5, 1.0, 2.5]
+    a, fa, _, sa = integrate_with_evolve(K, f, [1.0, 0.0], touts, evolve)
+    b, fb, sb = integrate(K, f, [1.0, 0.0], touts, rtol=1e-8, atol=1e-12)
+    assert fa == fb == [0, 0, 0] and len(calls) == 1
+    assert all(x.tobytes() == y.tobytes() for x, y in zip(a, b)) and sa["nst"] == sb["nst"]
+
+
+def test_evolve_hook_owns_the_loop_and_returns_permuted_vectors(K):
+    """A stand-in evolve that jumps to the exact solution just past tout: ARKode must take the state, the vector roles
+    (handles are swapped, not copied), the counters and the step size from it and interpolate to tout itself."""
+    f = make_rhs(K, lambda t, y: np.array([y[1], -y[0]]))
+    def put(v, vals):
+        p = K.N_VGetArrayPointer(v)
+        for i, x in enumerate(vals):
+            p[i] = x
+    def evolve(stp, user):
+        st = stp.contents
+        assert st.s == 5 and st.itask == 1 and st.next_h > 0 and st.nglobal == 2
+        assert abs(st.A[4][3] + 1.0 / 32.0) < 1e-16 and abs(st.d[4] - 16.0 / 3.0) < 1e-15     # Zonneveld 5-3-4, d = b - b_embedded
+        h = 1e-3
+        t1 = st.tout + 0.4 * h          # the accepted step [t1 - h, t1] brackets tout
+        t0 = t1 - h
+        # the new state goes into the caller's ycur array, the previous one stays where yn was: roles are permuted
+        put(st.ycur, [np.cos(t1), -np.sin(t1)]); put(st.yn, [np.cos(t0), -np.sin(t0)])
+        put(st.fold, [-np.sin(t1), -np.cos(t1)]); put(st.fnew, [-np.sin(t0), -np.cos(t0)])
+        st.yn, st.yold, st.ycur = st.ycur, st.yn, st.yold
+        st.fnew, st.fold = st.fold, st.fnew
+        st.tn, st.hold, st.next_h = t1, h, h
+        st.nst += 7; st.nst_attempts += 8; st.nfe += 40; st.netf += 1
+        st.flag = 0
+        return 0
+    touts = [0.5, 1.0, 2.5]
+    outs, flags, ts, st = integrate_with_evolve(K, f, [1.0, 0.0], touts, evolve)
+    assert flags == [0, 0, 0] and ts == touts
+    for tout, y in zip(touts, outs):
+        assert abs(y[0] - np.cos(tout)) < 1e-12 and abs(y[1] + np.sin(tout)) < 1e-12      # cubic Hermite over h = 1e-3
+    assert st["nst"] == 21 and st["nfe"] >= 120
+
+
+def test_evolve_hook_failures_are_reported_like_the_host_loop(K):
+    f = make_rhs(K, lambda t, y: np.array([y[1], -y[0]]))
+    def too_much_work(stp, user):
+        st = stp.contents
+        st.nst += st.max_steps
+        st.flag = -1
+        return 0
+    outs, flags, ts, st = integrate_with_evolve(K, f, [1.0, 0.0], [100.0], too_much_work, mxsteps=5)
+    assert flags == [-1] and ts == [0.0] and st["nst"] == 5 and outs[0].tolist() == [1.0, 0.0]
+    outs, flags, ts, st = integrate_with_evolve(K, f, [1.0, 0.0], [1.0], lambda stp, user: -1)
+    assert flags == [-20]       # ARK_MEM_FAIL: the device loop could not be launched
