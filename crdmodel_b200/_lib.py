@@ -30,7 +30,8 @@ class IcParams(C.Structure):
 
 
 class FusedOps(C.Structure):
-    _fields_ = [("lincomb", C.c_void_p), ("erk_finish", C.c_void_p), ("rhs_lincomb", C.c_void_p), ("erk_evolve", C.c_void_p)]
+    _fields_ = [("lincomb", C.c_void_p), ("erk_finish", C.c_void_p), ("rhs_lincomb", C.c_void_p), ("erk_evolve", C.c_void_p),
+                ("rhs_lincomb_finish", C.c_void_p)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, c_double_p, C.c_int, C.c_int, C.c_void_p)
@@ -76,6 +77,8 @@ SIGNATURES = {
     "crd_f": (I, [D, P, P, P]),
     "crd_rhs_lincomb": (I, [P, D, I, c_double_p, C.POINTER(P), P]),
     "crd_f_lincomb": (I, [D, I, c_double_p, C.POINTER(P), P, P]),
+    "crd_rhs_lincomb_finish": (I, [P, D, I, c_double_p, c_double_p, c_double_p, C.POINTER(P), P, D, D, c_double_p]),
+    "crd_f_lincomb_finish": (I, [D, I, c_double_p, c_double_p, c_double_p, C.POINTER(P), P, D, D, c_double_p, P]),
     "crd_grid_rhs_count": (C.c_int64, [P]),
     "crd_grid_set_variant": (I, [P, I]),
     "crd_grid_set_overlap": (I, [P, I]),
@@ -163,6 +166,7 @@ SIGNATURES = {
     "crd_ARKodeSetFusedOps": (I, [P, P]),
     "crd_ARKodeSetReuseFirstStage": (I, [P, I]),
     "crd_ARKodeSetResident": (I, [P, I]),
+    "crd_ARKodeSetStageFinish": (I, [P, I]),
     "crd_ARKodeSetInitStep": (I, [P, D]),
     "crd_ARKodeSetFixedStep": (I, [P, D]),
 }

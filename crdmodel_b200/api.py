@@ -258,6 +258,16 @@ class Grid:
         check(lib().crd_rhs_lincomb(self._h, t, n, (C.c_double * n)(*c), (C.c_void_p * n)(*[_ptr(x) for x in X]), _ptr(ydot)),
               "crd_rhs_lincomb")
 
+    def f_lincomb_finish(self, t, c, hb, hd, X, ynew, rtol, atol):
+        """Last RK stage fused with the step finish: returns (rc, sum (err w)^2, sum (ynew w')^2); rc = 1: does not apply."""
+        n = len(c)
+        out = (C.c_double * 2)()
+        rc = lib().crd_rhs_lincomb_finish(self._h, t, n, (C.c_double * n)(*c), (C.c_double * n)(*hb), (C.c_double * n)(*hd),
+                                          (C.c_void_p * n)(*[_ptr(x) for x in X]), _ptr(ynew), rtol, atol, out)
+        if rc < 0:
+            check(rc, "crd_rhs_lincomb_finish")
+        return rc, out[0], out[1]
+
     def post_halo(self, y):
         check(lib().crd_rhs_post_halo(self._h, _ptr(y)), "crd_rhs_post_halo")
 
@@ -294,7 +304,7 @@ class ARKodeSolver:
     """The reference's ARKode call sequence (FHNmodel_torus.cpp:356-373,423,491) over the device path."""
 
     def __init__(self, grid, y, t0=0.0, rtol=1e-5, atol=1e-10, max_steps=200000, fused=True, reuse_first_stage=False,
-                 resident=True):
+                 resident=True, stage_finish=True):
         L = lib()
         self.grid, self.y = grid, y
         self.mem = C.c_void_p(check_ptr(L.ARKodeCreate(), "ARKodeCreate"))
@@ -312,6 +322,8 @@ class ARKodeSolver:
         # resident: with the full fused table the whole step loop runs as one persistent kernel when it applies
         # (one GPU, mesh within the grid's size limit: Grid.set_resident); False keeps one launch per stage
         check(L.crd_ARKodeSetResident(self.mem, 1 if resident else 0), "crd_ARKodeSetResident")
+        # stage_finish: the last stage and the step finish in one pass over memory where the grid offers it (one GPU, large mesh)
+        check(L.crd_ARKodeSetStageFinish(self.mem, 1 if stage_finish else 0), "crd_ARKodeSetStageFinish")
 
     def set_init_step(self, h):
         check(lib().crd_ARKodeSetInitStep(self.mem, h), "crd_ARKodeSetInitStep")

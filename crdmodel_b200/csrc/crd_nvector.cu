@@ -315,8 +315,8 @@ struct _generic_N_Vector_Ops g_ops = {
     N_VDotProd_Crd, N_VMaxNorm_Crd, N_VWrmsNorm_Crd, N_VWrmsNormMask_Crd, N_VMin_Crd, N_VWL2Norm_Crd, N_VL1Norm_Crd,
     N_VCompare_Crd, N_VInvTest_Crd, N_VConstrMask_Crd, N_VMinQuotient_Crd};
 
-const crd_fused_ops g_fused = {N_VLinearCombination_Crd, N_VErkFinish_Crd, crd_f_lincomb, crd_erk_evolve};
-const crd_fused_ops g_fused_ops_only = {N_VLinearCombination_Crd, N_VErkFinish_Crd, nullptr, nullptr};
+const crd_fused_ops g_fused = {N_VLinearCombination_Crd, N_VErkFinish_Crd, crd_f_lincomb, crd_erk_evolve, crd_f_lincomb_finish};
+const crd_fused_ops g_fused_ops_only = {N_VLinearCombination_Crd, N_VErkFinish_Crd, nullptr, nullptr, nullptr};
 
 }  // namespace
 

@@ -312,6 +312,53 @@ int crd_f_lincomb(realtype t, int n, const realtype *c, N_Vector *X, N_Vector yd
   return crd_rhs_lincomb(g, t, n, c, xs, N_VGetDeviceArrayPointer_Crd(ydot)) == 0 ? 0 : -1;
 }
 
+// The last stage of an s-stage explicit RK step fused with the step finish: with X = (yn, F_0 .. F_{s-2}) and
+// F_{s-1} = f(t, sum_j c[j] X[j]) (never stored),  ynew = yn + sum_j hb[j] F_j,  err = sum_j hd[j] F_j,
+// out[0] = sum (err_i w_i)^2, out[1] = sum (ynew_i w'_i)^2 as N_VErkFinish_Crd defines them.  ynew has the bits of
+// crd_rhs_lincomb followed by N_VErkFinish_Crd.  Returns 1 when it does not apply (not 5 stages, a phi-split grid, a mesh
+// too small to stream): the caller then issues the two separate operations.
+int crd_rhs_lincomb_finish(crd_grid *g, double t, int s, const double *c, const double *hb, const double *hd,
+                           const double *const *X_dev, double *ynew_dev, double rtol, double atol, double out[2]) {
+  if (!g || !c || !hb || !hd || !X_dev || !ynew_dev || !out) { set_error("crd_rhs_lincomb_finish: null argument"); return -1; }
+  if (s != kMaxLc || g->connected || g->ctx->nranks > 1) return 1;
+  if (g->nx < 192 || g->nx * g->nyl < (1LL << 20)) return 1;
+  if (use(g->ctx)) return -1;
+  StateRef S;
+  S.n = s;
+  for (int j = 0; j < s; ++j) {
+    if (!X_dev[j] || X_dev[j] == ynew_dev) { set_error("crd_rhs_lincomb_finish: null or aliased vector"); return -1; }
+    S.x[j] = X_dev[j]; S.c[j] = c[j];
+  }
+  const long long nyl = g->nyl;
+  RhsArgs a = make_args(g, t, S, ynew_dev, 0, nyl, slab_row(nyl - 1), slab_row(0));
+  StageFin fin;
+  for (int j = 0; j < kMaxLc; ++j) { fin.hb[j] = hb[j]; fin.hd[j] = hd[j]; }
+  fin.rtol = rtol; fin.atol = atol; fin.partial = g->ctx->red_partial;
+  int nblocks = 0;
+  const int r = launch_stage_finish(g, a, fin, g->ctx->stream, &nblocks);
+  if (r != 0) return r;
+  fin_reduce_kernel<<<1, 256, 0, g->ctx->stream>>>(g->ctx->red_partial, nblocks, g->ctx->red_result_dev);
+  if (check_launch(g->ctx, "fin_reduce_kernel")) return -1;
+  CRD_CUDA(cudaStreamSynchronize(g->ctx->stream));
+  out[0] = g->ctx->red_result_host[0];
+  out[1] = g->ctx->red_result_host[1];
+  g->rhs_count++;
+  return 0;
+}
+
+int crd_f_lincomb_finish(realtype t, int s, const realtype *c, const realtype *hb, const realtype *hd, N_Vector *X, N_Vector ynew,
+                         realtype rtol, realtype atol, realtype out[2], void *user_data) {
+  crd_grid *g = (crd_grid *)user_data;
+  if (!g || !X || !ynew || s < 1 || s > kMaxLc) return -1;
+  const double *xs[kMaxLc];
+  for (int j = 0; j < s; ++j) {
+    xs[j] = N_VGetDeviceArrayPointer_Crd(X[j]);
+    if (!xs[j] || N_VGetLocalLength_Crd(X[j]) != crd_grid_local_length(g)) { set_error("crd_f_lincomb_finish: vector does not match the grid"); return -1; }
+  }
+  if (N_VGetLocalLength_Crd(ynew) != crd_grid_local_length(g)) { set_error("crd_f_lincomb_finish: vector does not match the grid"); return -1; }
+  return crd_rhs_lincomb_finish(g, t, s, c, hb, hd, xs, N_VGetDeviceArrayPointer_Crd(ynew), rtol, atol, out);
+}
+
 int crd_f(realtype t, N_Vector y, N_Vector ydot, void *user_data) {
   crd_grid *g = (crd_grid *)user_data;
   if (!g || !y || !ydot) return -1;

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <vector>
 
+#include "crd_fused.cuh"
 #include "crd_grid.cuh"
 #include "crd_rhs_point.cuh"
 
@@ -303,8 +304,18 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   }
 }
 
-template <int MODEL, bool EXACT, int NV, bool PLAIN, int RB>
-__global__ void __launch_bounds__(288, 2) rhs_stream_kernel(const RhsArgs a, int seg_rows, int S) {
+// FIN (the last stage of an explicit RK step, NV = s vectors yn, F_0 .. F_{s-2}): the stage derivative F_{s-1} is not stored;
+// instead, while it is in registers next to the raw yn and F_j of the same point, the consumer forms ynew = yn + sum hb_j F_j
+// (written to a.ydot), err = sum hd_j F_j and the two weighted square sums of erk_finish_kernel (crd_fused.cuh arithmetic, so
+// ynew has the same bits).  Saves the finish kernel's pass over s + 1 vectors: 112 of 528 B per point and step.
+struct StageFin {
+  double hb[kMaxLc], hd[kMaxLc];
+  double rtol, atol;
+  double *partial;   // [2][kRedBlocks] per-CTA sums
+};
+
+template <int MODEL, bool EXACT, int NV, bool PLAIN, int RB, bool FIN>
+__global__ void __launch_bounds__(288, 2) rhs_stream_kernel(const RhsArgs a, int seg_rows, int S, const StageFin fz) {
   constexpr int TX = 256, PITCH = TX + 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2 *ring = reinterpret_cast<double2 *>(smem_raw);                       // [S][RB][NV][PITCH]
@@ -370,6 +381,7 @@ __global__ void __launch_bounds__(288, 2) rhs_stream_kernel(const RhsArgs a, int
   const int c = threadIdx.x;   // 0..255: column inside the strip
   const int react_on = a.react;
   long long it = 0;
+  double fe2 = 0.0, fy2 = 0.0;   // FIN: this thread's share of sum (err w)^2, sum (ynew w')^2
   for (long long u = blockIdx.x; u < units; u += gridDim.x) {
     const long long strip = u % strips, seg = u / strips;
     const long long i0 = strip * TX, jA = seg * seg_rows, jB = (jA + seg_rows < nyl) ? jA + seg_rows : nyl;
@@ -383,15 +395,16 @@ __global__ void __launch_bounds__(288, 2) rhs_stream_kernel(const RhsArgs a, int
     double2 *out = reinterpret_cast<double2 *>(a.ydot) + jA * nx + (i0 + c);
     double uS = 0.0, cW = 0.0, cE = 0.0;
     double2 cc = make_double2(0.0, 0.0);
+    double2 pv[FIN ? NV : 1] = {};   // FIN: the raw vectors (yn, F_0 ..) of the row that is emitted next
     // one row: fetch (and combine) the arriving row jr, then emit row jr-1 from the three rows in registers
     auto step = [&](const double2 *slot, long long jr) {
       const bool ext = (jr < 0 && a.south) || (jr >= nyl && a.north);
       double2 nn;
       double nW, nE;
+      double2 v[NV];
       if (PLAIN || ext) {
         nn = slot[c + 1]; nW = slot[c].x; nE = slot[c + 2].x;
       } else {
-        double2 v[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) v[j] = slot[j * PITCH + c + 1];
         nn = make_double2(a.lc_c[0] * v[0].x, a.lc_c[0] * v[0].y);
@@ -418,10 +431,30 @@ __global__ void __launch_bounds__(288, 2) rhs_stream_kernel(const RhsArgs a, int
           du = frozen ? 0.0 : du;
           dv = frozen ? 0.0 : dv;
         }
-        if (active) *out = make_double2(du, dv);
+        if (!FIN) {
+          if (active) *out = make_double2(du, dv);
+        } else {
+          // ynew = yn + sum_j hb_j F_j, err = sum_j hd_j F_j with F_{NV-1} = (du, dv): the operation order of finish_elem
+          double sx = pv[0].x, sy = pv[0].y, ex = 0.0, ey = 0.0;
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            const double2 f = (j == NV - 1) ? make_double2(du, dv) : pv[j + 1 < NV ? j + 1 : 0];
+            sx = fma(fz.hb[j], f.x, sx); ex = fma(fz.hd[j], f.x, ex);
+            sy = fma(fz.hb[j], f.y, sy); ey = fma(fz.hd[j], f.y, ey);
+          }
+          if (active) {
+            *out = make_double2(sx, sy);
+            finish_tail(fz.rtol, fz.atol, pv[0].x, sx, ex, fe2, fy2);
+            finish_tail(fz.rtol, fz.atol, pv[0].y, sy, ey, fe2, fy2);
+          }
+        }
         out += nx;
       }
       uS = cc.x; cc = nn; cW = nW; cE = nE;
+      if (FIN) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) pv[j] = v[j];
+      }
     };
     for (long long j0 = jA - 1; j0 <= jB; j0 += RB, ++it) {
       const int s = (int)(it % S);
@@ -438,10 +471,42 @@ __global__ void __launch_bounds__(288, 2) rhs_stream_kernel(const RhsArgs a, int
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8u * (S + s)) : "memory");
     }
   }
+  if (FIN) {
+    // per-CTA sums in a fixed order: shuffle tree, then the eight consumer warps in order (the producer warp has left:
+    // named barrier over the 256 consumer threads)
+    __shared__ double fin_red[2][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { fe2 += __shfl_down_sync(0xffffffffu, fe2, o); fy2 += __shfl_down_sync(0xffffffffu, fy2, o); }
+    if (lane == 0) { fin_red[0][warp] = fe2; fin_red[1][warp] = fy2; }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (threadIdx.x == 0) {
+      double se = fin_red[0][0], sy = fin_red[1][0];
+      for (int w = 1; w < 8; ++w) { se += fin_red[0][w]; sy += fin_red[1][w]; }
+      fz.partial[blockIdx.x] = se;
+      fz.partial[kRedBlocks + blockIdx.x] = sy;
+    }
+  }
 }
 
-template <int MODEL, bool EXACT, int NV, bool PLAIN>
-int launch_stream_nv(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+// adds the per-CTA sums of a FIN stage in a fixed order; the two results go to mapped pinned host memory
+__global__ void __launch_bounds__(256) fin_reduce_kernel(const double *partial, int nblocks, double *result) {
+  __shared__ double sm[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double se = 0.0, sy = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += 256) { se += partial[b]; sy += partial[kRedBlocks + b]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { se += __shfl_down_sync(0xffffffffu, se, o); sy += __shfl_down_sync(0xffffffffu, sy, o); }
+  if (lane == 0) { sm[0][warp] = se; sm[1][warp] = sy; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { sm[0][0] += sm[0][w]; sm[1][0] += sm[1][w]; }
+    result[0] = sm[0][0]; result[1] = sm[1][0];
+    __threadfence_system();
+  }
+}
+
+template <int MODEL, bool EXACT, int NV, bool PLAIN, bool FIN = false>
+int launch_stream_nv(crd_grid *g, const RhsArgs &a, cudaStream_t st, const StageFin *fin = nullptr, int *nblocks = nullptr) {
   constexpr int RB = (NV == 1) ? 4 : (NV <= 3 ? 2 : 1);   // rows per ring stage
   const int seg_rows = 128;
   const long long strips = (a.nx + 255) / 256, segs = (a.nyl + seg_rows - 1) / seg_rows, units = strips * segs;
@@ -451,7 +516,7 @@ int launch_stream_nv(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   if (S > 8) S = 8;
   if (S < 3) S = 3;
   const size_t smem = (size_t)S * stage_bytes + (size_t)2 * S * 8;
-  auto kern = rhs_stream_kernel<MODEL, EXACT, NV, PLAIN, RB>;
+  auto kern = rhs_stream_kernel<MODEL, EXACT, NV, PLAIN, RB, FIN>;
   static bool attr_set[64] = {};   // the attribute is per device
   const int dev = g->ctx->device & 63;
   if (!attr_set[dev]) {
@@ -460,7 +525,10 @@ int launch_stream_nv(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
     attr_set[dev] = true;
   }
   const long long ctas = units < 2LL * kSMs ? units : 2LL * kSMs;
-  kern<<<(unsigned)ctas, 288, smem, st>>>(a, seg_rows, S);
+  StageFin fz;
+  if (fin) fz = *fin; else std::memset(&fz, 0, sizeof fz);
+  if (nblocks) *nblocks = (int)ctas;
+  kern<<<(unsigned)ctas, 288, smem, st>>>(a, seg_rows, S, fz);
   return check_launch(g->ctx, "rhs_stream_kernel");
 }
 
@@ -473,6 +541,21 @@ int launch_stream(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
     case 5: return launch_stream_nv<MODEL, EXACT, 5, false>(g, a, st);
     default: return 1;   // other counts: caller falls back to the tiled kernel
   }
+}
+
+// the last stage of a 5-stage method fused with the step finish (single slab); returns 1 when it does not apply
+int launch_stage_finish(crd_grid *g, const RhsArgs &a, const StageFin &fin, cudaStream_t st, int *nblocks) {
+  if (a.nlc != 5 || a.south || a.north) return 1;
+  const bool exact = g->p.arith == CRD_ARITH_EXACT;
+#define CRD_FIN(M) (exact ? launch_stream_nv<M, true, 5, false, true>(g, a, st, &fin, nblocks) : launch_stream_nv<M, false, 5, false, true>(g, a, st, &fin, nblocks))
+  switch (g->p.model) {
+    case CRD_FHN_TORUS: return CRD_FIN(CRD_FHN_TORUS);
+    case CRD_GOLDBETER_TORUS: return CRD_FIN(CRD_GOLDBETER_TORUS);
+    case CRD_FHN_FLAT: return CRD_FIN(CRD_FHN_FLAT);
+    case CRD_GOLDBETER_FLAT: return CRD_FIN(CRD_GOLDBETER_FLAT);
+  }
+#undef CRD_FIN
+  return 1;
 }
 
 template <int MODEL, bool EXACT>

@@ -62,6 +62,7 @@ struct ArkMem {
   bool reuse_first = false;
   bool resident = true;     // use fused->erk_evolve when it is offered and applies
   bool resident_na = false; // it answered "does not apply" once: stop asking
+  bool no_stage_finish = false;  // rhs_lincomb_finish answered "does not apply" once
 };
 
 void set_zonneveld(ArkMem *m) {
@@ -232,12 +233,37 @@ int take_step(ArkMem *m) {
     m->nst_attempts++;
     bool retry_rhs = false;
     for (int is = 0; is < m->s; ++is) m->Fp[is] = m->F[is];
+    bool finished = false;   // the last stage's evaluation also produced ynew and the error norm
+    double dsm_fused = 0;
     for (int is = 0; is < m->s; ++is) {
       if (is == 0 && m->reuse_first) {
         m->Fp[0] = m->fnew;  // f(tn, yn), evaluated when the previous step completed
         continue;
       }
       int r;
+      if (is == m->s - 1 && is > 0 && !m->no_stage_finish && m->fused && m->fused->rhs_lincomb_finish && m->fused->erk_finish &&
+          m->hfixed == 0.0) {
+        // last stage + finish in one pass, when every earlier stage enters the last one's state: X = (yn, F_0 .. F_{s-2})
+        bool dense = true;
+        for (int j = 0; j < is; ++j) dense = dense && m->A[is][j] != 0.0;
+        if (dense) {
+          double cc[S_MAX + 1], hb[S_MAX], hd[S_MAX], out[2] = {0, 0};
+          N_Vector XX[S_MAX + 1];
+          cc[0] = 1.0; XX[0] = m->yn;
+          for (int j = 0; j < is; ++j) { cc[j + 1] = m->h * m->A[is][j]; XX[j + 1] = m->Fp[j]; }
+          for (int j = 0; j < m->s; ++j) { hb[j] = m->h * m->b[j]; hd[j] = m->h * (m->b[j] - m->b2[j]); }
+          int fr = m->fused->rhs_lincomb_finish(m->tn + m->c[is] * m->h, m->s, cc, hb, hd, XX, m->ycur, m->rtol, m->atol, out, m->user_data);
+          if (fr < 0) return ARK_RHSFUNC_FAIL;
+          if (fr == 0) {
+            m->nfe++;
+            dsm_fused = std::sqrt(out[0] / (double)m->nglobal);
+            m->ynorm_sq_next = out[1];
+            finished = true;
+            continue;
+          }
+          m->no_stage_finish = true;   // does not apply to this problem: stop asking
+        }
+      }
       if (is > 0 && m->fused && m->fused->rhs_lincomb) {
         // stage state yn + h sum_j A_ij F_j formed inside the evaluation (zero coefficients dropped)
         double cc[S_MAX + 1];
@@ -271,9 +297,11 @@ int take_step(ArkMem *m) {
       }
     }
     if (retry_rhs) continue;
-    double dsm = 0;
-    int r = compute_solution(m, &dsm);
-    if (r != 0) return r;
+    double dsm = dsm_fused;
+    if (!finished) {
+      int r = compute_solution(m, &dsm);
+      if (r != 0) return r;
+    }
     if (m->hfixed != 0.0) { m->eta = 1.0; m->ehist[1] = m->ehist[0]; m->ehist[0] = dsm * m->bias; return 0; }
     m->eta = adapt_eta(m, dsm);
     if (dsm <= 1.0) {
@@ -429,6 +457,11 @@ int crd_ARKodeSetResident(void *mem, int on) {
   if (!mem) return ARK_MEM_NULL;
   ((ArkMem *)mem)->resident = on != 0;
   ((ArkMem *)mem)->resident_na = false;
+  return ARK_SUCCESS;
+}
+int crd_ARKodeSetStageFinish(void *mem, int on) {
+  if (!mem) return ARK_MEM_NULL;
+  ((ArkMem *)mem)->no_stage_finish = on == 0;
   return ARK_SUCCESS;
 }
 int crd_ARKodeSetInitStep(void *mem, realtype hin) {

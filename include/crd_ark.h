@@ -40,6 +40,11 @@ typedef struct crd_fused_ops {
    * (st->flag then holds what ARKode() would return before its dense-output evaluation), > 0 when it does not
    * apply to this problem (the integrator continues with its own host-driven loop), < 0 on a launch failure. */
   int (*erk_evolve)(struct crd_erk_state *st, void *user_data);
+  /* optional: the LAST stage and the step finish in one pass.  X = (yn, F_0 .. F_{s-2}); F_{s-1} = f(t, sum_j c[j] X[j]) is
+   * not stored; ynew and out[] as erk_finish defines them.  Returns 0, > 0 when it does not apply (the integrator then
+   * calls rhs_lincomb and erk_finish), < 0 on failure.  416 instead of 528 B/point/step. */
+  int (*rhs_lincomb_finish)(realtype t, int s, const realtype *c, const realtype *hb, const realtype *hd, N_Vector *X,
+                            N_Vector ynew, realtype rtol, realtype atol, realtype out[2], void *user_data);
 } crd_fused_ops;
 
 /* The integrator's state handed to erk_evolve and taken back from it.  The callee advances (tn, yn, fnew =
@@ -82,6 +87,9 @@ int crd_ARKodeSetReuseFirstStage(void *arkode_mem, int on);
  * operations offer it and it applies; on = 0 keeps the host-driven loop (one kernel launch per stage and a host
  * round trip per step). */
 int crd_ARKodeSetResident(void *arkode_mem, int on);
+/* Last stage + step finish in one pass (crd_fused_ops.rhs_lincomb_finish): on = 1 (default) uses it when offered and
+ * applicable; on = 0 always issues the stage evaluation and the finish separately. */
+int crd_ARKodeSetStageFinish(void *arkode_mem, int on);
 /* Initial step size (0 = estimate it, the default). */
 int crd_ARKodeSetInitStep(void *arkode_mem, realtype hin);
 /* Fixed step size (no error test, no adaptivity); 0 switches adaptivity back on. */

@@ -165,12 +165,12 @@ EVOLVE = C.CFUNCTYPE(C.c_int, C.POINTER(ErkState), P_)
 
 
 class FusedOps(C.Structure):
-    _fields_ = [("lincomb", P_), ("erk_finish", P_), ("rhs_lincomb", P_), ("erk_evolve", EVOLVE)]
+    _fields_ = [("lincomb", P_), ("erk_finish", P_), ("rhs_lincomb", P_), ("erk_evolve", EVOLVE), ("rhs_lincomb_finish", P_)]
 
 
 def integrate_with_evolve(K, f, y0, touts, evolve, mxsteps=200000):
     K.crd_ARKodeSetFusedOps.argtypes = [P_, C.POINTER(FusedOps)]
-    ops = FusedOps(None, None, None, EVOLVE(evolve))
+    ops = FusedOps(None, None, None, EVOLVE(evolve), None)
     y = np.array(y0, dtype=np.float64)
     Y = K.N_VMake_Parallel(0, y.size, y.size, y.ctypes.data)
     mem = P_(K.ARKodeCreate())

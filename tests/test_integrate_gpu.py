@@ -121,3 +121,27 @@ def test_fused_stage_rhs_does_not_change_the_trajectory(crd, ctx):
     assert res[0][0].tobytes() == res[1][0].tobytes()
     assert res[0][1]["nst"] == res[1][1]["nst"] and res[0][1]["nfe"] == res[1][1]["nfe"]
     assert res[1][2] < res[0][2]
+
+
+def test_fused_last_stage_finish_in_the_integrator(crd, ctx):
+    """Large single-GPU meshes: the host-driven loop issues the last stage and the finish as one kernel.  First step (given
+    h): the same bits as with the two separate kernels; afterwards the error norms differ by summation order only."""
+    nx, ny = 512, 2304      # > 1 Mi points: the fused kernel applies; > 4 Mi would be needed for nothing else
+    res = []
+    for sf in (False, True):
+        grid = crd.Grid(ctx, crd.make_params("fhn_torus", nx, ny, t_boundary=0.0))
+        grid.set_resident(-1)
+        y = grid.new_vector()
+        grid.fill_synthetic(y)
+        s = crd.ARKodeSolver(grid, y, fused="full", resident=False, stage_finish=sf)
+        s.set_init_step(1e-6)
+        flag, t = s.ARKode(1.0, crd.ARK_ONE_STEP)
+        assert flag == 0 and t == 1e-6
+        first = y.to_numpy()
+        for _ in range(5):
+            assert s.ARKode(1.0, crd.ARK_ONE_STEP)[0] == 0
+        res.append((first, y.to_numpy(), s.stats()))
+        s.free(); grid.close()
+    assert res[0][0].tobytes() == res[1][0].tobytes()
+    assert res[0][2]["nst"] == res[1][2]["nst"] == 6 and res[0][2]["nfe"] == res[1][2]["nfe"]
+    assert np.abs(res[0][1] - res[1][1]).max() <= 1e-9

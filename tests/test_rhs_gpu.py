@@ -232,3 +232,39 @@ def test_fused_stage_rhs_equals_lincomb_then_rhs(crd, ctx, oracle, model):
                     g.f_lincomb(t, coefs, V, d2)
                     assert d1.to_numpy().tobytes() == d2.to_numpy().tobytes(), (model, nx, ny, ncomb, variant, t)
                 g.close()
+
+
+@pytest.mark.parametrize("model,arith", [("fhn_torus", "exact"), ("fhn_torus", "fast"), ("gb_torus", "exact"), ("fhn_flat", "exact"), ("gb_flat", "fast")])
+def test_last_stage_fused_with_the_finish_equals_stage_then_finish(crd, ctx, model, arith):
+    """crd_rhs_lincomb_finish (streaming kernel, F_5 never stored) against crd_rhs_lincomb followed by N_VErkFinish_Crd:
+    ynew bit-identical, the two weighted square sums equal to summation-order rounding; ragged strip and row counts;
+    frozen rows (t < tBoundary)."""
+    nx, ny = 520, 2100          # > 1 Mi points, 3 strips (the last one 8 columns wide), rows not a multiple of the segments
+    ar = crd.ARITH_EXACT if arith == "exact" else crd.ARITH_FAST
+    grid = crd.Grid(ctx, crd.make_params(model, nx, ny, arith=ar, t_boundary=38.0))
+    rng = np.random.default_rng(7)
+    n = 2 * nx * ny
+    lo, hi = (-2.0, 2.0) if model.startswith("fhn") else (0.1, 1.6)
+    X = [crd.NVector.from_numpy(ctx, rng.uniform(lo, hi, n))] + [crd.NVector.from_numpy(ctx, rng.uniform(-1.0, 1.0, n)) for _ in range(4)]
+    h = 1e-3
+    c = [1.0, h * 5 / 32, h * 7 / 32, h * 13 / 32, -h / 32]
+    hb = [h / 6, h / 3, h / 3, h / 6, 0.0]
+    hd = [h * (1 / 6 + 0.5), h * (1 / 3 - 7 / 3), h * (1 / 3 - 7 / 3), h * (1 / 6 - 13 / 6), h * 16 / 3]
+    rtol, atol = 1e-5, 1e-10
+    for t in (10.0, 50.0):
+        F5, want, got = grid.new_vector(), grid.new_vector(), grid.new_vector()
+        grid.f_lincomb(t, c, X, F5)
+        e2, y2 = crd.N_VErkFinish(hb, hd, X[0], X[1:] + [F5], want, rtol, atol)
+        rc, fe2, fy2 = grid.f_lincomb_finish(t, c, hb, hd, X, got, rtol, atol)
+        assert rc == 0
+        assert got.to_numpy().tobytes() == want.to_numpy().tobytes()
+        assert abs(fe2 - e2) <= 1e-11 * e2 and abs(fy2 - y2) <= 1e-11 * y2
+        for v in (F5, want, got):
+            v.destroy()
+    # does not apply: small meshes (the caller issues the two operations)
+    small = crd.Grid(ctx, crd.make_params(model, 64, 96, arith=ar))
+    Xs = [small.new_vector() for _ in range(5)]
+    for v in Xs:
+        crd.N_VConst(0.5, v)
+    assert small.f_lincomb_finish(50.0, c, hb, hd, Xs, small.new_vector(), rtol, atol)[0] == 1
+    small.close(); grid.close()
