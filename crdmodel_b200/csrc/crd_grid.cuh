@@ -89,6 +89,7 @@ struct crd_grid {
   unsigned long long computed = 0;   // epoch of the last compute
   int64_t rhs_count = 0;
   int variant = 0;
+  double *fin_partial = nullptr;   // per-CTA sums of a stage fused with the step finish: 3 launches x [2][kRedBlocks]
   // device-resident step loop (crd_resident.cu): -1 off, 0 automatic (meshes that live in L2), 1 always
   int resident = 0;
   int64_t resident_launches = 0;

@@ -114,6 +114,7 @@ void crd_grid_destroy(crd_grid *g) {
   if (g->prev_ipc && g->halo_prev) cudaIpcCloseMemHandle(g->halo_prev);
   if (g->next_ipc && g->halo_next && g->halo_next != g->halo_prev) cudaIpcCloseMemHandle(g->halo_next);
   cudaFree(g->cth); cudaFree(g->brow); cudaFree(g->halo_local); cudaFree(g->push_ticket);
+  if (g->fin_partial) cudaFree(g->fin_partial);
   if (g->res_bar) cudaFree(g->res_bar);
   if (g->res_partial) cudaFree(g->res_partial);
   if (g->res_out_host) cudaFreeHost(g->res_out_host);
@@ -232,12 +233,30 @@ static int post_state(crd_grid *g, const StateRef &S) {
   return launch_push(g, S, g->s_aux);
 }
 
-static int compute_state(crd_grid *g, double t, const StateRef &S, double *ydot) {
+// Last stage fused with the step finish: every launch of the evaluation writes its per-CTA sums into its own region.
+struct FinCtx {
+  StageFin fin;          // fin.partial = base of region 0
+  int nregions = 0;
+  int nblocks[3] = {0, 0, 0};
+};
+constexpr int kFinRegion = 2 * kRedBlocks;   // doubles per region: [2][kRedBlocks]
+
+static int launch_part(crd_grid *g, const RhsArgs &a, cudaStream_t st, FinCtx *fc) {
+  if (!fc) return launch_rhs(g, a, st);
+  StageFin f = fc->fin;
+  f.partial = fc->fin.partial + (size_t)fc->nregions * kFinRegion;
+  const int r = launch_stage_finish(g, a, f, st, &fc->nblocks[fc->nregions]);
+  if (r != 0) { if (r > 0) set_error("fused stage finish: kernel not available for this launch"); return -1; }
+  fc->nregions++;
+  return 0;
+}
+
+static int compute_state(crd_grid *g, double t, const StateRef &S, double *ydot, FinCtx *fc = nullptr) {
   cudaStream_t st = g->ctx->stream;
   const long long nyl = g->nyl, B = kEdgeRows;
   if (!g->connected) {
     RhsArgs a = make_args(g, t, S, ydot, 0, nyl, slab_row(nyl - 1), slab_row(0));
-    if (launch_rhs(g, a, st)) return -1;
+    if (launch_part(g, a, st, fc)) return -1;
     g->rhs_count++;
     return 0;
   }
@@ -249,16 +268,16 @@ static int compute_state(crd_grid *g, double t, const StateRef &S, double *ydot)
   if (!g->split) {
     if (launch_wait(g, st)) return -1;
     RhsArgs a = make_args(g, t, S, ydot, 0, nyl, ext_row(gs), ext_row(gn));
-    if (launch_rhs(g, a, st)) return -1;
+    if (launch_part(g, a, st, fc)) return -1;
   } else {
     // interior rows on the main stream: their neighbours are rows of this slab
     RhsArgs ai = make_args(g, t, S, ydot, B, nyl - B, slab_row(B - 1), slab_row(nyl - B));
-    if (launch_rhs(g, ai, st)) return -1;
+    if (launch_part(g, ai, st, fc)) return -1;
     // edge rows on the auxiliary stream, once the neighbours' rows of this epoch have landed
     if (launch_wait(g, g->s_aux)) return -1;
     RhsArgs as = make_args(g, t, S, ydot, 0, B, ext_row(gs), slab_row(B));
     RhsArgs an = make_args(g, t, S, ydot, nyl - B, nyl, slab_row(nyl - B - 1), ext_row(gn));
-    if (launch_rhs(g, as, g->s_aux) || launch_rhs(g, an, g->s_aux)) return -1;
+    if (launch_part(g, as, g->s_aux, fc) || launch_part(g, an, g->s_aux, fc)) return -1;
     CRD_CUDA(cudaEventRecord(g->ev_b, g->s_aux));
     CRD_CUDA(cudaStreamWaitEvent(st, g->ev_b, 0));
   }
@@ -320,29 +339,29 @@ int crd_f_lincomb(realtype t, int n, const realtype *c, N_Vector *X, N_Vector yd
 int crd_rhs_lincomb_finish(crd_grid *g, double t, int s, const double *c, const double *hb, const double *hd,
                            const double *const *X_dev, double *ynew_dev, double rtol, double atol, double out[2]) {
   if (!g || !c || !hb || !hd || !X_dev || !ynew_dev || !out) { set_error("crd_rhs_lincomb_finish: null argument"); return -1; }
-  if (s != kMaxLc || g->connected || g->ctx->nranks > 1) return 1;
-  if (g->nx < 192 || g->nx * g->nyl < (1LL << 20)) return 1;
-  if (use(g->ctx)) return -1;
+  // decided before anything is posted to the neighbours: 5 stages, a mesh the streaming kernel is made for
+  if (s != kMaxLc || g->nx < 192 || g->nx * g->nyl < (1LL << 20)) return 1;
+  crd_ctx *ctx = g->ctx;
+  if (use(ctx)) return -1;
   StateRef S;
   S.n = s;
   for (int j = 0; j < s; ++j) {
     if (!X_dev[j] || X_dev[j] == ynew_dev) { set_error("crd_rhs_lincomb_finish: null or aliased vector"); return -1; }
     S.x[j] = X_dev[j]; S.c[j] = c[j];
   }
-  const long long nyl = g->nyl;
-  RhsArgs a = make_args(g, t, S, ynew_dev, 0, nyl, slab_row(nyl - 1), slab_row(0));
-  StageFin fin;
-  for (int j = 0; j < kMaxLc; ++j) { fin.hb[j] = hb[j]; fin.hd[j] = hd[j]; }
-  fin.rtol = rtol; fin.atol = atol; fin.partial = g->ctx->red_partial;
-  int nblocks = 0;
-  const int r = launch_stage_finish(g, a, fin, g->ctx->stream, &nblocks);
-  if (r != 0) return r;
-  fin_reduce_kernel<<<1, 256, 0, g->ctx->stream>>>(g->ctx->red_partial, nblocks, g->ctx->red_result_dev);
-  if (check_launch(g->ctx, "fin_reduce_kernel")) return -1;
-  CRD_CUDA(cudaStreamSynchronize(g->ctx->stream));
-  out[0] = g->ctx->red_result_host[0];
-  out[1] = g->ctx->red_result_host[1];
-  g->rhs_count++;
+  if (!g->fin_partial) CRD_CUDA(cudaMalloc(&g->fin_partial, sizeof(double) * 3 * kFinRegion));
+  FinCtx fc;
+  for (int j = 0; j < kMaxLc; ++j) { fc.fin.hb[j] = hb[j]; fc.fin.hd[j] = hd[j]; }
+  fc.fin.rtol = rtol; fc.fin.atol = atol; fc.fin.partial = g->fin_partial;
+  if (post_state(g, S)) return -1;
+  if (compute_state(g, t, S, ynew_dev, &fc)) return -1;
+  // every launch has been joined into the main stream: add the regions in a fixed order
+  fin_reduce_kernel<<<1, 256, 0, ctx->stream>>>(g->fin_partial, fc.nregions, fc.nblocks[0], fc.nblocks[1], fc.nblocks[2], ctx->red_result_dev);
+  if (check_launch(ctx, "fin_reduce_kernel")) return -1;
+  CRD_CUDA(cudaStreamSynchronize(ctx->stream));
+  out[0] = ctx->red_result_host[0];
+  out[1] = ctx->red_result_host[1];
+  if (ctx->nranks > 1 && ctx->allreduce(out, 2, CRD_SUM, ctx->allreduce_user) != 0) { set_error("crd_rhs_lincomb_finish: allreduce hook failed"); return -1; }
   return 0;
 }
 

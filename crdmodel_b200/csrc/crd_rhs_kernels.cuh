@@ -488,12 +488,17 @@ __global__ void __launch_bounds__(288, 2) rhs_stream_kernel(const RhsArgs a, int
   }
 }
 
-// adds the per-CTA sums of a FIN stage in a fixed order; the two results go to mapped pinned host memory
-__global__ void __launch_bounds__(256) fin_reduce_kernel(const double *partial, int nblocks, double *result) {
+// adds the per-CTA sums of a FIN stage (up to three launches, one region of [2][kRedBlocks] each) in a fixed order; the two
+// results go to mapped pinned host memory
+__global__ void __launch_bounds__(256) fin_reduce_kernel(const double *partial, int nregions, int n0, int n1, int n2, double *result) {
   __shared__ double sm[2][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double se = 0.0, sy = 0.0;
-  for (int b = threadIdx.x; b < nblocks; b += 256) { se += partial[b]; sy += partial[kRedBlocks + b]; }
+  for (int r = 0; r < nregions; ++r) {
+    const double *p = partial + (size_t)r * 2 * kRedBlocks;
+    const int n = r == 0 ? n0 : r == 1 ? n1 : n2;
+    for (int b = threadIdx.x; b < n; b += 256) { se += p[b]; sy += p[kRedBlocks + b]; }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { se += __shfl_down_sync(0xffffffffu, se, o); sy += __shfl_down_sync(0xffffffffu, sy, o); }
   if (lane == 0) { sm[0][warp] = se; sm[1][warp] = sy; }
@@ -543,9 +548,10 @@ int launch_stream(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   }
 }
 
-// the last stage of a 5-stage method fused with the step finish (single slab); returns 1 when it does not apply
+// the last stage of a 5-stage method fused with the step finish (one launch of it: a whole slab, or the interior / an edge band
+// of a phi-split one, ghost rows included); returns 1 when it does not apply
 int launch_stage_finish(crd_grid *g, const RhsArgs &a, const StageFin &fin, cudaStream_t st, int *nblocks) {
-  if (a.nlc != 5 || a.south || a.north) return 1;
+  if (a.nlc != 5) return 1;
   const bool exact = g->p.arith == CRD_ARITH_EXACT;
 #define CRD_FIN(M) (exact ? launch_stream_nv<M, true, 5, false, true>(g, a, st, &fin, nblocks) : launch_stream_nv<M, false, 5, false, true>(g, a, st, &fin, nblocks))
   switch (g->p.model) {

@@ -144,7 +144,8 @@ int crd_f_lincomb(realtype t, int n, const realtype *c, N_Vector *X, N_Vector yd
 /* The last stage of a 5-stage explicit RK step fused with the step finish (ARKode's stage evaluation + arkComputeSolutions
  * + the WRMS error norm inside ARKode() :423): X = (yn, F_0 .. F_3), F_4 = f(t, sum_j c[j] X[j]) is never stored,
  * ynew = yn + sum_j hb[j] F_j, err = sum_j hd[j] F_j, out[] = the two weighted square sums of N_VErkFinish_Crd.  Returns
- * 0, or 1 when it does not apply (phi-split grid, mesh too small to stream, s != 5): issue the two operations separately. */
+ * 0, or 1 when it does not apply (mesh too small to stream, s != 5): issue the two operations separately.  On a phi-split
+ * grid it posts the halo rows of the stage state like crd_rhs_lincomb and sums out[] over the ranks. */
 int crd_rhs_lincomb_finish(crd_grid *g, double t, int s, const double *c, const double *hb, const double *hd,
                            const double *const *X_dev, double *ynew_dev, double rtol, double atol, double out[2]);
 int crd_f_lincomb_finish(realtype t, int s, const realtype *c, const realtype *hb, const realtype *hd, N_Vector *X, N_Vector ynew,

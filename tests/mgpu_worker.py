@@ -62,6 +62,39 @@ def main():
             dist.barrier()
             ctx.sync()
             grid.close()
+    # last RK stage fused with the step finish over the ring (interior + two edge-band launches, each with its own region
+    # of partial sums) == stage evaluation then N_VErkFinish: ynew bit for bit, the global sums to rounding
+    for model in ("fhn_torus", "gb_torus"):
+        nx, rows = 320, 3400                       # > 1 Mi points per rank: the streaming kernel applies
+        ny = rows * world
+        js, je = crd.decomp_phi(ny, world, rank)
+        grid = crd.Grid(ctx, crd.make_params(model, nx, ny, js=js, je=je, t_boundary=38.0))
+        cdist.ring_connect(grid, rank, world, cdist.exchange_handles(grid.halo_handle()))
+        X = []
+        for k in range(5):
+            v = grid.new_vector()
+            grid.fill_synthetic(v, seed=0x5EED + k)
+            if k > 0:
+                crd.N_VScale(0.25, v, v)
+            X.append(v)
+        h = 1e-3
+        c = [1.0, h * 5 / 32, h * 7 / 32, h * 13 / 32, -h / 32]
+        hb = [h / 6, h / 3, h / 3, h / 6, 0.0]
+        hd = [h * (1 / 6 + 0.5), h * (1 / 3 - 7 / 3), h * (1 / 3 - 7 / 3), h * (1 / 6 - 13 / 6), h * 16 / 3]
+        good = True
+        for t in (10.0, 50.0):
+            F5, want, got = grid.new_vector(), grid.new_vector(), grid.new_vector()
+            grid.f_lincomb(t, c, X, F5)
+            e2, y2 = crd.N_VErkFinish(hb, hd, X[0], X[1:] + [F5], want, 1e-5, 1e-10)
+            rc, fe2, fy2 = grid.f_lincomb_finish(t, c, hb, hd, X, got, 1e-5, 1e-10)
+            good = good and rc == 0 and got.to_numpy().tobytes() == want.to_numpy().tobytes()
+            good = good and abs(fe2 - e2) <= 1e-11 * e2 and abs(fy2 - y2) <= 1e-11 * y2
+        if not good:
+            print("rank %d: FAILED fused stage finish %s" % (rank, model), flush=True)
+        ok = ok and good
+        dist.barrier()
+        ctx.sync()
+        grid.close()
     # trajectory: phi-split integration == single-slab CPU integration of the same driver
     nx, ny = 32, 128
     beta = 1.25
