@@ -679,7 +679,14 @@ int crd_erk_evolve(struct crd_erk_state *st, void *user_data) {
   CRD_CUDA(cudaMemsetAsync(g->res_bar, 0, 32 * sizeof(unsigned long long), ctx->stream));
   void *kargs[] = {(void *)&P};
   cudaError_t e = cudaLaunchCooperativeKernel(K->fn, dim3((unsigned)nb), dim3(K->threads), kargs, dyn_smem, ctx->stream);
-  if (e != cudaSuccess) { set_error("crd_erk_evolve: cooperative launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return -1; }
+  if (e != cudaSuccess) {
+    // nothing has run: the integrator can carry on with its launch-per-stage loop (e.g. the CTAs cannot all be
+    // co-resident because another context occupies SMs); do not ask again for this grid
+    set_error("crd_erk_evolve: cooperative launch failed (%s): falling back to the host-driven loop", cudaGetErrorString(e));
+    cudaGetLastError();
+    g->resident = -1;
+    return 1;
+  }
   ctx->launches++;
   g->resident_launches++;
   CRD_CUDA(cudaStreamSynchronize(ctx->stream));
