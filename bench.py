@@ -176,6 +176,7 @@ def default_mesh_integrations(crd, ctx):
         fhn = model.startswith("fhn")
         beta = 1.25 if fhn else 0.4
         row = {"model": model, "nx": nx, "ny": ny, "t_final": tf}
+        # op_by_op re-evaluates f(tn, yn) as stage 1 like ARKode 1.x (6 evaluations per step); the fused loops reuse it (5)
         for name, fused, resident in (("resident", "full", True), ("host_driven_fused", "full", False), ("op_by_op", False, False)):
             g = crd.Grid(ctx, crd.make_params(model, nx, ny, beta=beta, vary_beta=0, t_boundary=0.0))
             y = g.new_vector()
@@ -358,7 +359,7 @@ def main():
             integ = {"steps_per_s": (n1["nst"] - n0["nst"]) / dt, "step_attempts_per_s": (n1["nst_attempts"] - n0["nst_attempts"]) / dt,
                      "nst": n1["nst"] - n0["nst"], "nfe": n1["nfe"] - n0["nfe"], "netf": n1["netf"] - n0["netf"],
                      "rhs_per_step": (n1["nfe"] - n0["nfe"]) / max(1, n1["nst_attempts"] - n0["nst_attempts"]),
-                     "flag": flag, "method": "Zonneveld 5-3-4 explicit RK, rtol 1e-5 atol 1e-10, host-driven loop (mesh beyond L2: the resident loop does not apply), stage assembly fused into the RHS kernels, last stage fused with the step finish"}
+                     "flag": flag, "method": "Zonneveld 5-3-4 explicit RK, rtol 1e-5 atol 1e-10, host-driven loop (mesh beyond L2: the resident loop does not apply), stage assembly fused into the RHS kernels, last stage fused with the step finish, f(tn, yn) of the previous step reused as stage 1 (bit-identical to re-evaluating it as ARKode 1.x does: 5 instead of 6 evaluations per step)"}
             solver.free()
         except Exception as e:  # the headline metric does not depend on this block
             integ = {"error": str(e)[:200]}

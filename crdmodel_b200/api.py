@@ -303,7 +303,7 @@ class Grid:
 class ARKodeSolver:
     """The reference's ARKode call sequence (FHNmodel_torus.cpp:356-373,423,491) over the device path."""
 
-    def __init__(self, grid, y, t0=0.0, rtol=1e-5, atol=1e-10, max_steps=200000, fused=True, reuse_first_stage=False,
+    def __init__(self, grid, y, t0=0.0, rtol=1e-5, atol=1e-10, max_steps=200000, fused=True, reuse_first_stage=None,
                  resident=True, stage_finish=True):
         L = lib()
         self.grid, self.y = grid, y
@@ -318,6 +318,11 @@ class ARKodeSolver:
         if fused:
             table = L.crd_nv_fused_vector_ops() if fused == "ops" else L.crd_nv_fused_ops()
             check(L.crd_ARKodeSetFusedOps(self.mem, C.cast(table, C.c_void_p)), "crd_ARKodeSetFusedOps")
+        # stage 1 of every step is f(tn, yn), which the previous step has just evaluated for its dense output: with the
+        # fused operations it is reused by default (bit-identical results, 5 instead of 6 evaluations per step); the
+        # op-by-op sequence re-evaluates it like ARKode 1.x does
+        if reuse_first_stage is None:
+            reuse_first_stage = bool(fused)
         check(L.crd_ARKodeSetReuseFirstStage(self.mem, 1 if reuse_first_stage else 0), "crd_ARKodeSetReuseFirstStage")
         # resident: with the full fused table the whole step loop runs as one persistent kernel when it applies
         # (one GPU, mesh within the grid's size limit: Grid.set_resident); False keeps one launch per stage

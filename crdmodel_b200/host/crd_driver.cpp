@@ -12,7 +12,7 @@
 // Ranks are GPUs: `System.gpus = G` (or CRD_GPUS=G) forks G worker processes, one per GPU, each owning a
 // phi slab; neighbours' boundary rows travel through CUDA-IPC peer mappings, norms through shared memory.
 // New optional keys (absent => the reference's behaviour): System.gpus, System.arith (exact|fast),
-// System.fused (1), System.reuseFirstStage (0), System.resident (1), Parameters.phiMesh, Parameters.Zs / Ys.
+// System.fused (1), System.reuseFirstStage (= fused), System.resident (1), Parameters.phiMesh, Parameters.Zs / Ys.
 #include <pthread.h>
 #include <sys/mman.h>
 #include <sys/wait.h>
@@ -172,7 +172,7 @@ Config read_config(const char *path) {
   const std::string ar = pt.has("System.arith") ? pt.str("System.arith") : "exact";
   c.arith = (ar == "fast") ? CRD_ARITH_FAST : CRD_ARITH_EXACT;
   c.fused = pt.get<int>("System.fused", 1);
-  c.reuse = pt.get<int>("System.reuseFirstStage", 0);
+  c.reuse = pt.get<int>("System.reuseFirstStage", c.fused ? 1 : 0);   // f(tn, yn) is already there from the previous step: same bits
   c.resident = pt.get<int>("System.resident", 1);   // 1: the step loop runs as one persistent kernel when it applies
   if (!kFhn) {
     if (pt.has("Parameters.Zs") && pt.has("Parameters.Ys")) {

@@ -100,8 +100,8 @@ def test_trajectory_matches_the_host_driven_loop(crd, ctx, model):
     print("\n%s host-driven nst=%d nfe=%d netf=%d | resident nst=%d nfe=%d netf=%d" %
           (model, sa["nst"], sa["nfe"], sa["netf"], sb["nst"], sb["nfe"], sb["netf"]))
     assert abs(sa["nst"] - sb["nst"]) <= max(2, sa["nst"] // 50)
-    # the resident loop never re-evaluates f(tn, yn) as stage 1: s evaluations per attempt instead of s + 1
-    assert sb["nfe"] <= sa["nfe"]
+    # neither loop re-evaluates f(tn, yn) as stage 1: s evaluations per attempt; the attempts differ by a few rejections
+    assert abs(sb["nfe"] - sa["nfe"]) <= max(10, sa["nfe"] // 20)
     assert abs(sa["hlast"] - sb["hlast"]) <= 0.05 * abs(sa["hlast"])
 
 
