@@ -146,6 +146,16 @@ def test_default_meshes_use_the_resident_loop_and_large_ones_do_not(crd, ctx):
     s = crd.ARKodeSolver(grid, y)
     assert s.ARKode(0.01)[0] == 0 and grid.resident_launches == 1
     s.free(); grid.close()
+    # a band whose stage tile does not fit shared memory (14 rows x 1024 columns x 16 B = 229 KB): not applicable even when
+    # asked for; the integrator carries on with the launch-per-stage loop by itself
+    grid = crd.Grid(ctx, crd.make_params("fhn_torus", 1024, 2048))
+    grid.set_resident(1)
+    y = grid.new_vector()
+    grid.fill_synthetic(y)
+    s = crd.ARKodeSolver(grid, y)
+    assert s.ARKode(1.0, crd.ARK_ONE_STEP)[0] == 0 and s.ARKode(1.0, crd.ARK_ONE_STEP)[0] == 0 and grid.resident_launches == 0
+    assert s.stats()["nst"] == 2
+    s.free(); grid.close()
     nx, ny = 2048, 2304    # > 4 Mi points: HBM-bound, stays with the TMA-tiled launch-per-stage path
     grid = crd.Grid(ctx, crd.make_params("fhn_torus", nx, ny))
     y = grid.new_vector()
