@@ -113,7 +113,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
-template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, bool LC, int NG>
+template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, bool LC, int NG, bool LCT = false>
 __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   constexpr int PITCH = TX + 2;            // points per staged row (west halo + TX + east halo)
   constexpr int RPT = TY * TX / 256;       // rows marched by one thread
@@ -121,8 +121,9 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   constexpr int GR = (TY + 2 + NG - 1) / NG;
   static_assert(256 % TX == 0 && (TY * TX) % 256 == 0, "tile shape");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double2 *tile = reinterpret_cast<double2 *>(smem_raw);                      // [TY+2][PITCH]
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)(TY + 2) * PITCH * 16);
+  double2 *tile = reinterpret_cast<double2 *>(smem_raw);                      // [TY+2][PITCH]  (LCT: one such tile per input vector)
+  constexpr size_t kTileBytes = (size_t)(TY + 2) * PITCH * 16;
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + kTileBytes * (LCT ? (size_t)a.nlc : 1));
 
   const long long nx = a.nx, nyl = a.nyl;
   const long long tiles_x = (nx + TX - 1) / TX;
@@ -159,6 +160,62 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
     }
   }
   __syncthreads();   // barrier initialised before anyone polls it
+  } else if (LCT) {
+    // fused stage assembly, TMA-staged: the raw tile of EVERY input vector arrives by 1-D bulk copies (no thread computes a
+    // load address, no registers hold data in flight); when all have landed the CTA folds them into the first tile in the
+    // operation order of state2<true> / lincomb_kernel, and the march below runs on that tile as on a plain state.
+    const int nv = a.nlc;
+    const bool ext_s = (j0 == 0) && a.south != nullptr, ext_n = (j0 + h == nyl) && a.north != nullptr;   // already combined ghost rows
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const bool west_in = i0 > 0, east_in = i0 + w < nx;
+      const unsigned row_bytes = (unsigned)(w + (west_in ? 1 : 0) + (east_in ? 1 : 0)) * 16u;
+      unsigned total = 0;
+      for (int r = 0; r < h + 2; ++r) {
+        const bool ext = (r == 0 && ext_s) || (r == h + 1 && ext_n);
+        total += (unsigned)(ext ? 1 : nv) * (unsigned)(w + 2) * 16u;
+      }
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+      for (int r = 0; r < h + 2; ++r) {
+        const long long jr = j0 - 1 + r;
+        const bool ext = (r == 0 && ext_s) || (r == h + 1 && ext_n);
+        for (int j = 0; j < (ext ? 1 : nv); ++j) {
+          const double2 *row;
+          if (ext) row = reinterpret_cast<const double2 *>(jr < 0 ? a.south : a.north);
+          else row = reinterpret_cast<const double2 *>(a.lc_x[j]) + ((jr < 0) ? a.south_off : (jr >= nyl) ? a.north_off : jr * nx);
+          const unsigned dst = smem_u32(smem_raw + kTileBytes * j) + (unsigned)(r * PITCH) * 16u;
+          bulk_g2s(dst + (west_in ? 0u : 16u), row + i0 - (west_in ? 1 : 0), row_bytes, bar);
+          if (!west_in) bulk_g2s(dst, row + (nx - 1), 16u, bar);
+          if (!east_in) bulk_g2s(dst + (unsigned)(w + 1) * 16u, row, 16u, bar);
+        }
+      }
+    }
+    __syncthreads();   // barrier initialised before anyone polls it
+    {
+      unsigned ok = 0;
+      while (!ok) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar) : "memory");
+      }
+    }
+    const int cols = w + 2;
+    for (int e = threadIdx.x; e < (h + 2) * cols; e += 256) {
+      const int r = e / cols, sc = e - r * cols;
+      if ((r == 0 && ext_s) || (r == h + 1 && ext_n)) continue;
+      const int idx = r * PITCH + sc;
+      const double2 v0 = tile[idx];
+      double2 sacc = make_double2(a.lc_c[0] * v0.x, a.lc_c[0] * v0.y);
+#pragma unroll
+      for (int j = 1; j < kMaxLc; ++j) {
+        if (j < nv) {
+          const double2 v = reinterpret_cast<const double2 *>(smem_raw + kTileBytes * j)[idx];
+          sacc.x = fma(a.lc_c[j], v.x, sacc.x); sacc.y = fma(a.lc_c[j], v.y, sacc.y);
+        }
+      }
+      tile[idx] = sacc;
+    }
+    __syncthreads();
   } else {
     // fused stage assembly: the tile is the combination sum_j c_j x_j, formed while it is staged (the stage
     // state is never written to HBM).  Plain coalesced 16-byte loads; each thread stages its own column, nine
@@ -283,6 +340,27 @@ int launch_tile_lc(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   kern<<<(unsigned)tiles, 256, smem, st>>>(a);
   return check_launch(g->ctx, "rhs_tile_kernel");
 }
+// fused stage assembly with TMA-staged raw tiles (2 or 3 input vectors; 128 x 8 tiles: 21 KB per vector, 4 CTAs per SM for 2).
+// Experimental (variant 30): bit-identical, measured slower than the register-staged tile (profiles/README.md)
+template <int MODEL, bool EXACT>
+int launch_tile_lct(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
+  constexpr int TX = 128, TY = 8;
+  const long long tiles = ((a.nx + TX - 1) / TX) * ((a.nyl + TY - 1) / TY);
+  if (tiles <= 0) return 0;
+  if (tiles > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
+  const size_t smem = (size_t)(TY + 2) * (TX + 2) * 16 * (size_t)a.nlc + 16;
+  auto kern = rhs_tile_kernel<MODEL, EXACT, TX, TY, 4, false, true, 1, true>;
+  static int attr_set[64] = {};   // per device: the largest size set so far
+  const int dev = g->ctx->device & 63;
+  if (attr_set[dev] < (int)smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+    attr_set[dev] = (int)smem;
+  }
+  kern<<<(unsigned)tiles, 256, smem, st>>>(a);
+  return check_launch(g->ctx, "rhs_tile_kernel");
+}
+
 template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, int NG = 3>
 int launch_tile(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   return a.nlc > 0 ? launch_tile_lc<MODEL, EXACT, TX, TY, MINB, ACC, true, 1>(g, a, st)
@@ -581,6 +659,10 @@ int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
   // measured (profiles/README.md): the streaming kernel wins only for the widest fused stage (5 input vectors,
   // where its once-per-row fetch beats the tiled kernel's register-staged tiles); the tiled kernel everywhere else
   if (g->variant == 0 && a_in.nlc == 5 && a_in.nx >= 192 && a_in.nx * a_in.nyl >= (4LL << 20)) variant = 20;
+  if (variant == 30) {   // fused stage assembly with TMA-staged raw tiles (2 or 3 input vectors)
+    if (a_in.nlc == 2 || a_in.nlc == 3) return launch_tile_lct<MODEL, EXACT>(g, a_in, st);
+    variant = 13;
+  }
   if (variant == 20) {   // streaming kernel (persistent CTAs, shared-memory row ring)
     const int r = launch_stream<MODEL, EXACT>(g, a_in, st);
     if (r <= 0) return r;
