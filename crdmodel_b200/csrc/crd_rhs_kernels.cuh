@@ -392,8 +392,8 @@ struct StageFin {
   double *partial;   // [2][kRedBlocks] per-CTA sums
 };
 
-template <int MODEL, bool EXACT, int NV, bool PLAIN, int RB, bool FIN>
-__global__ void __launch_bounds__(288, 2) rhs_stream_kernel(const RhsArgs a, int seg_rows, int S, const StageFin fz) {
+template <int MODEL, bool EXACT, int NV, bool PLAIN, int RB, bool FIN, int MINB = 2>
+__global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, int seg_rows, int S, const StageFin fz) {
   constexpr int TX = 256, PITCH = TX + 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2 *ring = reinterpret_cast<double2 *>(smem_raw);                       // [S][RB][NV][PITCH]
@@ -588,18 +588,19 @@ __global__ void __launch_bounds__(256) fin_reduce_kernel(const double *partial, 
   }
 }
 
-template <int MODEL, bool EXACT, int NV, bool PLAIN, bool FIN = false>
+// MINB = CTAs per SM: 2 (ring of ~100 KB, up to 113 registers) or 3 (ring of ~66 KB, up to 75 registers: 24 consumer warps per SM)
+template <int MODEL, bool EXACT, int NV, bool PLAIN, bool FIN = false, int MINB = 2>
 int launch_stream_nv(crd_grid *g, const RhsArgs &a, cudaStream_t st, const StageFin *fin = nullptr, int *nblocks = nullptr) {
   constexpr int RB = (NV == 1) ? 4 : (NV <= 3 ? 2 : 1);   // rows per ring stage
   const int seg_rows = 128;
   const long long strips = (a.nx + 255) / 256, segs = (a.nyl + seg_rows - 1) / seg_rows, units = strips * segs;
   if (units <= 0) return 0;
   const size_t stage_bytes = (size_t)RB * NV * 258 * 16;
-  int S = (int)(100000 / stage_bytes);
+  int S = (int)((MINB == 3 ? 68000 : 100000) / stage_bytes);
   if (S > 8) S = 8;
   if (S < 3) S = 3;
   const size_t smem = (size_t)S * stage_bytes + (size_t)2 * S * 8;
-  auto kern = rhs_stream_kernel<MODEL, EXACT, NV, PLAIN, RB, FIN>;
+  auto kern = rhs_stream_kernel<MODEL, EXACT, NV, PLAIN, RB, FIN, MINB>;
   static bool attr_set[64] = {};   // the attribute is per device
   const int dev = g->ctx->device & 63;
   if (!attr_set[dev]) {
@@ -607,7 +608,7 @@ int launch_stream_nv(crd_grid *g, const RhsArgs &a, cudaStream_t st, const Stage
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
     attr_set[dev] = true;
   }
-  const long long ctas = units < 2LL * kSMs ? units : 2LL * kSMs;
+  const long long ctas = units < (long long)MINB * kSMs ? units : (long long)MINB * kSMs;
   StageFin fz;
   if (fin) fz = *fin; else std::memset(&fz, 0, sizeof fz);
   if (nblocks) *nblocks = (int)ctas;
@@ -662,6 +663,11 @@ int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
   if (variant == 30) {   // fused stage assembly with TMA-staged raw tiles (2 or 3 input vectors)
     if (a_in.nlc == 2 || a_in.nlc == 3) return launch_tile_lct<MODEL, EXACT>(g, a_in, st);
     variant = 13;
+  }
+  if (variant == 21) {   // streaming kernel with 3 CTAs per SM (2 or 3 input vectors)
+    if (a_in.nlc == 2) return launch_stream_nv<MODEL, EXACT, 2, false, false, 3>(g, a_in, st);
+    if (a_in.nlc == 3) return launch_stream_nv<MODEL, EXACT, 3, false, false, 3>(g, a_in, st);
+    variant = 20;
   }
   if (variant == 20) {   // streaming kernel (persistent CTAs, shared-memory row ring)
     const int r = launch_stream<MODEL, EXACT>(g, a_in, st);

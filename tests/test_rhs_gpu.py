@@ -221,7 +221,7 @@ def test_fused_stage_rhs_equals_lincomb_then_rhs(crd, ctx, oracle, model):
         n_el = 2 * nx * ny
         X = [oracle.fill_state(model, n_el, seed=40 + j) for j in range(5)]
         for ncomb, coefs in ((1, [1.0]), (2, [1.0, 0.013]), (3, [1.0, 0.02, -0.007]), (5, [1.0, 0.004, 0.005, 0.009, -0.001])):
-            for variant in (0, 1, 5, 10, 13, 20, 30):
+            for variant in (0, 1, 5, 10, 13, 20, 21, 30):
                 g = crd.Grid(ctx, crd.make_params(model, nx, ny, t_boundary=38.0))
                 g.set_variant(variant)
                 V = [crd.NVector.from_numpy(ctx, x) for x in X[:ncomb]]
