@@ -161,61 +161,38 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   }
   __syncthreads();   // barrier initialised before anyone polls it
   } else if (LCT) {
-    // fused stage assembly, TMA-staged: the raw tile of EVERY input vector arrives by 1-D bulk copies (no thread computes a
-    // load address, no registers hold data in flight); when all have landed the CTA folds them into the first tile in the
-    // operation order of state2<true> / lincomb_kernel, and the march below runs on that tile as on a plain state.
+    // fused stage assembly, TMA-staged: the raw tile of EVERY input vector arrives by 1-D bulk copies in the same NG row
+    // groups as a plain state (no thread computes a load address, no registers hold data in flight, no staging pass); the
+    // march below forms sum_j c_j x_j of each value it reads, in the operation order of state2<true> / lincomb_kernel.
     const int nv = a.nlc;
     const bool ext_s = (j0 == 0) && a.south != nullptr, ext_n = (j0 + h == nyl) && a.north != nullptr;   // already combined ghost rows
     if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+#pragma unroll
+      for (int gi = 0; gi < NG; ++gi) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8u * gi) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       const bool west_in = i0 > 0, east_in = i0 + w < nx;
       const unsigned row_bytes = (unsigned)(w + (west_in ? 1 : 0) + (east_in ? 1 : 0)) * 16u;
-      unsigned total = 0;
-      for (int r = 0; r < h + 2; ++r) {
-        const bool ext = (r == 0 && ext_s) || (r == h + 1 && ext_n);
-        total += (unsigned)(ext ? 1 : nv) * (unsigned)(w + 2) * 16u;
-      }
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
-      for (int r = 0; r < h + 2; ++r) {
-        const long long jr = j0 - 1 + r;
-        const bool ext = (r == 0 && ext_s) || (r == h + 1 && ext_n);
-        for (int j = 0; j < (ext ? 1 : nv); ++j) {
-          const double2 *row;
-          if (ext) row = reinterpret_cast<const double2 *>(jr < 0 ? a.south : a.north);
-          else row = reinterpret_cast<const double2 *>(a.lc_x[j]) + ((jr < 0) ? a.south_off : (jr >= nyl) ? a.north_off : jr * nx);
-          const unsigned dst = smem_u32(smem_raw + kTileBytes * j) + (unsigned)(r * PITCH) * 16u;
-          bulk_g2s(dst + (west_in ? 0u : 16u), row + i0 - (west_in ? 1 : 0), row_bytes, bar);
-          if (!west_in) bulk_g2s(dst, row + (nx - 1), 16u, bar);
-          if (!east_in) bulk_g2s(dst + (unsigned)(w + 1) * 16u, row, 16u, bar);
+      for (int gi = 0; gi < NG; ++gi) {
+        const int ra = gi * GR, rb = (ra + GR < h + 2) ? ra + GR : h + 2;
+        unsigned gbytes = 0;
+        for (int r = ra; r < rb; ++r) gbytes += (unsigned)(((r == 0 && ext_s) || (r == h + 1 && ext_n)) ? 1 : nv) * (unsigned)(w + 2) * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar + 8u * gi), "r"(gbytes) : "memory");
+        for (int r = ra; r < rb; ++r) {
+          const long long jr = j0 - 1 + r;
+          const bool ext = (r == 0 && ext_s) || (r == h + 1 && ext_n);
+          for (int j = 0; j < (ext ? 1 : nv); ++j) {
+            const double2 *row;
+            if (ext) row = reinterpret_cast<const double2 *>(jr < 0 ? a.south : a.north);
+            else row = reinterpret_cast<const double2 *>(a.lc_x[j]) + ((jr < 0) ? a.south_off : (jr >= nyl) ? a.north_off : jr * nx);
+            const unsigned dst = smem_u32(smem_raw + kTileBytes * j) + (unsigned)(r * PITCH) * 16u;
+            bulk_g2s(dst + (west_in ? 0u : 16u), row + i0 - (west_in ? 1 : 0), row_bytes, bar + 8u * gi);
+            if (!west_in) bulk_g2s(dst, row + (nx - 1), 16u, bar + 8u * gi);
+            if (!east_in) bulk_g2s(dst + (unsigned)(w + 1) * 16u, row, 16u, bar + 8u * gi);
+          }
         }
       }
     }
-    __syncthreads();   // barrier initialised before anyone polls it
-    {
-      unsigned ok = 0;
-      while (!ok) {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(bar) : "memory");
-      }
-    }
-    const int cols = w + 2;
-    for (int e = threadIdx.x; e < (h + 2) * cols; e += 256) {
-      const int r = e / cols, sc = e - r * cols;
-      if ((r == 0 && ext_s) || (r == h + 1 && ext_n)) continue;
-      const int idx = r * PITCH + sc;
-      const double2 v0 = tile[idx];
-      double2 sacc = make_double2(a.lc_c[0] * v0.x, a.lc_c[0] * v0.y);
-#pragma unroll
-      for (int j = 1; j < kMaxLc; ++j) {
-        if (j < nv) {
-          const double2 v = reinterpret_cast<const double2 *>(smem_raw + kTileBytes * j)[idx];
-          sacc.x = fma(a.lc_c[j], v.x, sacc.x); sacc.y = fma(a.lc_c[j], v.y, sacc.y);
-        }
-      }
-      tile[idx] = sacc;
-    }
-    __syncthreads();
+    __syncthreads();   // barriers initialised before anyone polls them
   } else {
     // fused stage assembly: the tile is the combination sum_j c_j x_j, formed while it is staged (the stage
     // state is never written to HBM).  Plain coalesced 16-byte loads; each thread stages its own column, nine
@@ -277,14 +254,39 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
     }
   };
   // rows g0, g0+1, g0+2 of the tile are needed before the first output row
-  if (!LC) {
+  if (!LC || LCT) {
     for (int gi = 0; gi <= (g0 + 2) / GR; ++gi) wait_group(gi);
   }
   if (!active) return;
 
   const double2 *col = tile + (g0 + 1) * PITCH + (c + 1);   // centre of this thread's first row
-  double uS = col[-PITCH].x;
-  double2 cc = col[0];
+  // LCT: the value at tile offset `off` (relative to col) is the combination of the raw tiles; row `tr` of the tile may be
+  // a ghost row that arrived already combined (ring: first tile only)
+  const bool lct_ext_s = LCT && (j0 == 0) && a.south != nullptr, lct_ext_n = LCT && (j0 + h == nyl) && a.north != nullptr;
+  auto rd2 = [&](int off, int tr) -> double2 {
+    const double2 v0 = col[off];
+    if (!LCT) return v0;
+    if ((tr == 0 && lct_ext_s) || (tr == h + 1 && lct_ext_n)) return v0;
+    double2 sacc = make_double2(a.lc_c[0] * v0.x, a.lc_c[0] * v0.y);
+#pragma unroll
+    for (int j = 1; j < kMaxLc; ++j)
+      if (j < a.nlc) {
+        const double2 v = reinterpret_cast<const double2 *>(reinterpret_cast<const unsigned char *>(col) + kTileBytes * j)[off];
+        sacc.x = fma(a.lc_c[j], v.x, sacc.x); sacc.y = fma(a.lc_c[j], v.y, sacc.y);
+      }
+    return sacc;
+  };
+  auto rdx = [&](int off) -> double {   // u only, never a ghost row (west / east neighbours of the thread's own rows)
+    const double v0 = col[off].x;
+    if (!LCT) return v0;
+    double sacc = a.lc_c[0] * v0;
+#pragma unroll
+    for (int j = 1; j < kMaxLc; ++j)
+      if (j < a.nlc) sacc = fma(a.lc_c[j], reinterpret_cast<const double2 *>(reinterpret_cast<const unsigned char *>(col) + kTileBytes * j)[off].x, sacc);
+    return sacc;
+  };
+  double uS = rd2(-PITCH, g0).x;
+  double2 cc = rd2(0, g0 + 1);
   double2 *out = reinterpret_cast<double2 *>(a.ydot) + (j0 + g0) * nx + (i0 + c);
   const int nrows = (h - g0 < RPT) ? (h - g0) : RPT;
   const double *__restrict__ brow = a.brow + (j0 + g0);
@@ -292,9 +294,9 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   double2 *const out0 = out;
   bool bad = (ACC && EXACT && is_torus(MODEL)) ? (a.k.div_safe == 0) : false;
   auto row = [&](int r) {
-    if (!LC && r > 0 && (g0 + r + 2) % GR == 0 && (g0 + r + 2) / GR < NG) wait_group((g0 + r + 2) / GR);   // north row enters a new group
-    const double2 nn = col[(r + 1) * PITCH];
-    const double uW = col[r * PITCH - 1].x, uE = col[r * PITCH + 1].x;
+    if ((!LC || LCT) && r > 0 && (g0 + r + 2) % GR == 0 && (g0 + r + 2) / GR < NG) wait_group((g0 + r + 2) / GR);   // north row enters a new group
+    const double2 nn = rd2((r + 1) * PITCH, g0 + r + 2);
+    const double uW = rdx(r * PITCH - 1), uE = rdx(r * PITCH + 1);
     double du = !EXACT ? stencil_fast<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x)
                 : ACC  ? stencil_exact_acc<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x, bad)
                        : stencil_exact<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x);
@@ -340,16 +342,16 @@ int launch_tile_lc(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   kern<<<(unsigned)tiles, 256, smem, st>>>(a);
   return check_launch(g->ctx, "rhs_tile_kernel");
 }
-// fused stage assembly with TMA-staged raw tiles (2 or 3 input vectors; 128 x 8 tiles: 21 KB per vector, 4 CTAs per SM for 2).
-// Experimental (variant 30): bit-identical, measured slower than the register-staged tile (profiles/README.md)
+// fused stage assembly with TMA-staged raw tiles (2 or 3 input vectors; 128 x 16 tiles: 37 KB per vector, 3 CTAs per SM for 2),
+// the combination formed during the march (variant 30)
 template <int MODEL, bool EXACT>
 int launch_tile_lct(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
-  constexpr int TX = 128, TY = 8;
+  constexpr int TX = 128, TY = 16, NG = 3;
   const long long tiles = ((a.nx + TX - 1) / TX) * ((a.nyl + TY - 1) / TY);
   if (tiles <= 0) return 0;
   if (tiles > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
-  const size_t smem = (size_t)(TY + 2) * (TX + 2) * 16 * (size_t)a.nlc + 16;
-  auto kern = rhs_tile_kernel<MODEL, EXACT, TX, TY, 4, false, true, 1, true>;
+  const size_t smem = (size_t)(TY + 2) * (TX + 2) * 16 * (size_t)a.nlc + 8 * NG + 8;
+  auto kern = rhs_tile_kernel<MODEL, EXACT, TX, TY, 3, false, true, NG, true>;
   static int attr_set[64] = {};   // per device: the largest size set so far
   const int dev = g->ctx->device & 63;
   if (attr_set[dev] < (int)smem) {
@@ -660,6 +662,8 @@ int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
   // measured (profiles/README.md): the streaming kernel wins only for the widest fused stage (5 input vectors,
   // where its once-per-row fetch beats the tiled kernel's register-staged tiles); the tiled kernel everywhere else
   if (g->variant == 0 && a_in.nlc == 5 && a_in.nx >= 192 && a_in.nx * a_in.nyl >= (4LL << 20)) variant = 20;
+  // 2 or 3 input vectors: the streaming kernel with 3 CTAs per SM (24 consumer warps) is 1-3 % / 13-15 % ahead of the staged tile
+  if (g->variant == 0 && (a_in.nlc == 2 || a_in.nlc == 3) && a_in.nx >= 192 && a_in.nx * a_in.nyl >= (4LL << 20)) variant = 21;
   if (variant == 30) {   // fused stage assembly with TMA-staged raw tiles (2 or 3 input vectors)
     if (a_in.nlc == 2 || a_in.nlc == 3) return launch_tile_lct<MODEL, EXACT>(g, a_in, st);
     variant = 13;
