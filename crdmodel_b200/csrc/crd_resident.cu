@@ -279,7 +279,7 @@ __device__ double res_adapt_eta(const ResArgs &P, double hcur, double dsm, doubl
   return h_acc / hcur;
 }
 
-template <int MODEL, bool EXACT, int NT>
+template <int MODEL, bool EXACT, int NT, bool TICKS>
 __global__ void __launch_bounds__(NT, 1) erk_resident_kernel(const ResArgs P) {
   constexpr int NW = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_dyn[];   // [stage tile][storage 0] .. [storage nslots-1]
@@ -348,8 +348,8 @@ __global__ void __launch_bounds__(NT, 1) erk_resident_kernel(const ResArgs P) {
   // where the time goes, as seen by thread 0 (reported for CTA 0): cycles since the previous tick are booked on `k`
   long long cyc[5] = {0, 0, 0, 0, 0}, t_last = clock64();
   const long long t_begin = t_last;
-  auto tick = [&](int k) {
-    if (threadIdx.x == 0) { const long long now = clock64(); cyc[k] += now - t_last; t_last = now; }
+  auto tick = [&](int k) {   // TICKS = false (the default kernel): nothing — the counters cost 14 registers and 3 % of a step
+    if (TICKS && threadIdx.x == 0) { const long long now = clock64(); cyc[k] += now - t_last; t_last = now; }
   };
   if (threadIdx.x == 0) {
     L.tn = P.tn; L.next_h = P.next_h; L.h = P.next_h; L.hold = P.hold; L.eta = P.eta; L.etamax = P.etamax;
@@ -541,25 +541,26 @@ struct ResKernel {
   int static_smem[64];   // per device: 0 = not asked yet, -1 = cannot run here, else static shared bytes + 1
 };
 
-template <int MODEL, bool EXACT, int NT>
+template <int MODEL, bool EXACT, int NT, bool TICKS>
 ResKernel *res_kernel_entry() {
-  static ResKernel k = {(const void *)erk_resident_kernel<MODEL, EXACT, NT>, NT, {}};
+  static ResKernel k = {(const void *)erk_resident_kernel<MODEL, EXACT, NT, TICKS>, NT, {}};
   return &k;
 }
 
 // 512 threads per CTA, 128 registers per thread.  Measured on the 400 x 1600 mesh: 1024 threads x 64 registers shorten
 // the stencil phase by 20 % but spill, lengthen every other phase and lose 5 % per step.
+// ticks: the instantiation with per-phase cycle counters (crd_grid_resident_cycles), selected by grid variant 150
 template <int MODEL, bool EXACT>
-ResKernel *res_pick_nt(int) {
-  return res_kernel_entry<MODEL, EXACT, 512>();
+ResKernel *res_pick_nt(int ticks) {
+  return ticks ? res_kernel_entry<MODEL, EXACT, 512, true>() : res_kernel_entry<MODEL, EXACT, 512, false>();
 }
 
-ResKernel *res_pick(int model, bool exact, int nt) {
+ResKernel *res_pick(int model, bool exact, int ticks) {
   switch (model) {
-    case CRD_FHN_TORUS: return exact ? res_pick_nt<CRD_FHN_TORUS, true>(nt) : res_pick_nt<CRD_FHN_TORUS, false>(nt);
-    case CRD_GOLDBETER_TORUS: return exact ? res_pick_nt<CRD_GOLDBETER_TORUS, true>(nt) : res_pick_nt<CRD_GOLDBETER_TORUS, false>(nt);
-    case CRD_FHN_FLAT: return exact ? res_pick_nt<CRD_FHN_FLAT, true>(nt) : res_pick_nt<CRD_FHN_FLAT, false>(nt);
-    case CRD_GOLDBETER_FLAT: return exact ? res_pick_nt<CRD_GOLDBETER_FLAT, true>(nt) : res_pick_nt<CRD_GOLDBETER_FLAT, false>(nt);
+    case CRD_FHN_TORUS: return exact ? res_pick_nt<CRD_FHN_TORUS, true>(ticks) : res_pick_nt<CRD_FHN_TORUS, false>(ticks);
+    case CRD_GOLDBETER_TORUS: return exact ? res_pick_nt<CRD_GOLDBETER_TORUS, true>(ticks) : res_pick_nt<CRD_GOLDBETER_TORUS, false>(ticks);
+    case CRD_FHN_FLAT: return exact ? res_pick_nt<CRD_FHN_FLAT, true>(ticks) : res_pick_nt<CRD_FHN_FLAT, false>(ticks);
+    case CRD_GOLDBETER_FLAT: return exact ? res_pick_nt<CRD_GOLDBETER_FLAT, true>(ticks) : res_pick_nt<CRD_GOLDBETER_FLAT, false>(ticks);
   }
   return nullptr;
 }
@@ -634,7 +635,7 @@ int crd_erk_evolve(struct crd_erk_state *st, void *user_data) {
   P.tn = st->tn; P.next_h = st->next_h; P.hold = st->hold; P.eta = st->eta; P.etamax = st->etamax;
   P.eh0 = st->ehist[0]; P.eh1 = st->ehist[1]; P.ynorm_sq = st->ynorm_sq;
 
-  ResKernel *K = res_pick(g->p.model, g->p.arith == CRD_ARITH_EXACT, 512);
+  ResKernel *K = res_pick(g->p.model, g->p.arith == CRD_ARITH_EXACT, g->variant == 150 ? 1 : 0);
   if (!K) { set_error("crd_erk_evolve: unknown model"); return -1; }
   const int dev = ctx->device & 63;
   int sms = 0, smem_optin = 0;

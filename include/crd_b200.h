@@ -167,7 +167,8 @@ int crd_grid_set_resident(crd_grid *g, int mode);
 /* how many times the resident loop was launched on this grid */
 int64_t crd_grid_resident_launches(const crd_grid *g);
 /* where the last resident launch spent its SM cycles, as seen by one CTA: phase 1 (stage state), interior rows,
- * grid-barrier wait, edge rows, everything else, total */
+ * grid-barrier wait, edge rows, everything else, total.  Counted only by the profiling instantiation of the kernel
+ * (crd_grid_set_variant(g, 150): 14 more registers, 3 % slower); the default kernel reports the total only. */
 int crd_grid_resident_cycles(const crd_grid *g, int64_t out[6]);
 
 /* ---- synthetic states and initial conditions --------------------------------------------------- */

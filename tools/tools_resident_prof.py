@@ -5,7 +5,7 @@ import crdmodel_b200 as crd
 model = sys.argv[1] if len(sys.argv) > 1 else "fhn_torus"
 nx, ny = (400, 1600) if model.startswith("fhn") else (100, 400)
 tf = float(sys.argv[2]) if len(sys.argv) > 2 else 0.3
-variant = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+variant = int(sys.argv[3]) if len(sys.argv) > 3 else 150   # 150: the instantiation with per-phase cycle counters; 0: the default kernel
 ctx = crd.Context(0)
 beta = 1.25 if model.startswith("fhn") else 0.4
 g = crd.Grid(ctx, crd.make_params(model, nx, ny, beta=beta, vary_beta=0, t_boundary=0.0))
