@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libcrd_b200.so")
+# CRD_B200_LIB: another build of the same library (kernel experiments); there is still no fallback of any kind
+LIB_PATH = os.environ.get("CRD_B200_LIB") or os.path.join(HERE, "lib", "libcrd_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_long_p = C.POINTER(C.c_long)
