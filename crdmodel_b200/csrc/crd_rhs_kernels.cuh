@@ -458,97 +458,121 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
   }
 
   // ---------------- consumers ----------------
+  // A thread owns one column and walks the rows of the unit as they arrive: row jr comes in (loaded, combined, its west /
+  // east u taken from the neighbouring lanes), row jr-1 goes out from the three rows held in registers.  Only the first two
+  // and the last row of a unit can be anything special (an already combined ghost row, no output yet, a frozen boundary row):
+  // they take the checked path; every other row takes the lean one (the kernel is issue-bound: profiles/README.md).
   const int c = threadIdx.x;   // 0..255: column inside the strip
   const int react_on = a.react;
-  long long it = 0;
+  const int nxi = (int)nx, nyli = (int)nyl;
+  int slot_i = 0;
+  unsigned slot_par = 0;
   double fe2 = 0.0, fy2 = 0.0;   // FIN: this thread's share of sum (err w)^2, sum (ynew w')^2
+  double lcc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) lcc[j] = a.lc_c[j];
+  const bool edge_lane = (lane == 0) || (lane == 31);
+  const int edge_q = (lane == 0) ? c : c + 2;   // slot index of the neighbour column that lives in another warp
   for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-    const long long strip = u % strips, seg = u / strips;
-    const long long i0 = strip * TX, jA = seg * seg_rows, jB = (jA + seg_rows < nyl) ? jA + seg_rows : nyl;
-    const int w = (nx - i0 < TX) ? (int)(nx - i0) : TX;
+    const int strip = (int)(u % strips), seg = (int)(u / strips);
+    const int i0 = strip * TX, jA = seg * seg_rows, jB = (jA + seg_rows < nyli) ? jA + seg_rows : nyli;
+    const int w = (nxi - i0 < TX) ? (nxi - i0) : TX;
     const bool active = c < w;
     double t1 = 0.0, t3 = 0.0;
     if (is_torus(MODEL) && active) {
       const double2 tc = reinterpret_cast<const double2 *>(a.cth)[i0 + c];
       t1 = tc.x; t3 = tc.y;
     }
-    double2 *out = reinterpret_cast<double2 *>(a.ydot) + jA * nx + (i0 + c);
+    double2 *out = reinterpret_cast<double2 *>(a.ydot) + (long long)jA * nx + (i0 + c);
+    const double *bp = a.brow + jA;   // beta of the next row to go out
     double uS = 0.0, cW = 0.0, cE = 0.0;
     double2 cc = make_double2(0.0, 0.0);
-    double2 pv[FIN ? NV : 1] = {};   // FIN: the raw vectors (yn, F_0 ..) of the row that is emitted next
-    // one row: fetch (and combine) the arriving row jr, then emit row jr-1 from the three rows in registers
-    auto step = [&](const double2 *slot, long long jr) {
-      const bool ext = (jr < 0 && a.south) || (jr >= nyl && a.north);
-      double2 nn;
-      double nW, nE;
-      double2 v[NV];
+    double2 pv[FIN ? NV : 1] = {};   // FIN: the raw vectors (yn, F_0 ..) of the row that goes out next
+    // the arriving row: nn (combined centre), nW / nE (combined u of the neighbours), v (raw vectors, FIN)
+    auto fetch = [&](const double2 *slot, bool ext, double2 &nn, double &nW, double &nE, double2 (&v)[NV]) {
       if (PLAIN || ext) {
         nn = slot[c + 1]; nW = slot[c].x; nE = slot[c + 2].x;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = nn;
       } else {
 #pragma unroll
         for (int j = 0; j < NV; ++j) v[j] = slot[j * PITCH + c + 1];
-        nn = make_double2(a.lc_c[0] * v[0].x, a.lc_c[0] * v[0].y);
+        nn = make_double2(lcc[0] * v[0].x, lcc[0] * v[0].y);
 #pragma unroll
-        for (int j = 1; j < NV; ++j) { nn.x = fma(a.lc_c[j], v[j].x, nn.x); nn.y = fma(a.lc_c[j], v[j].y, nn.y); }
+        for (int j = 1; j < NV; ++j) { nn.x = fma(lcc[j], v[j].x, nn.x); nn.y = fma(lcc[j], v[j].y, nn.y); }
         nW = __shfl_up_sync(0xffffffffu, nn.x, 1);
         nE = __shfl_down_sync(0xffffffffu, nn.x, 1);
-        if (lane == 0 || lane == 31) {   // the neighbour lives in another warp: combine its u from the slot
-          const int q = (lane == 0) ? c : c + 2;
-          double e = a.lc_c[0] * slot[q].x;
+        if (edge_lane) {   // the neighbour lives in another warp: combine its u from the slot
+          double e = lcc[0] * slot[edge_q].x;
 #pragma unroll
-          for (int j = 1; j < NV; ++j) e = fma(a.lc_c[j], slot[j * PITCH + q].x, e);
+          for (int j = 1; j < NV; ++j) e = fma(lcc[j], slot[j * PITCH + edge_q].x, e);
           if (lane == 0) nW = e; else nE = e;
         }
       }
-      if (jr > jA) {   // rows jr-2 (uS), jr-1 (cc) and jr (nn) are here: output row jr-1
-        const long long jl = jr - 1;
-        double du = EXACT ? stencil_exact<MODEL>(a.k, t1, t3, cc.x, cW, cE, uS, nn.x)
-                          : stencil_fast<MODEL>(a.k, t1, t3, cc.x, cW, cE, uS, nn.x);
-        double dv = 0.0;
-        if (react_on) {
-          react<MODEL, EXACT>(a.k, __ldg(a.brow + jl), cc.x, cc.y, du, dv);
-          const bool frozen = (a.freeze_north && jl == nyl - 1) || (a.freeze_south && jl == 0);
-          du = frozen ? 0.0 : du;
-          dv = frozen ? 0.0 : dv;
-        }
-        if (!FIN) {
-          if (active) *out = make_double2(du, dv);
-        } else {
-          // ynew = yn + sum_j hb_j F_j, err = sum_j hd_j F_j with F_{NV-1} = (du, dv): the operation order of finish_elem
-          double sx = pv[0].x, sy = pv[0].y, ex = 0.0, ey = 0.0;
-#pragma unroll
-          for (int j = 0; j < NV; ++j) {
-            const double2 f = (j == NV - 1) ? make_double2(du, dv) : pv[j + 1 < NV ? j + 1 : 0];
-            sx = fma(fz.hb[j], f.x, sx); ex = fma(fz.hd[j], f.x, ex);
-            sy = fma(fz.hb[j], f.y, sy); ey = fma(fz.hd[j], f.y, ey);
-          }
-          if (active) {
-            *out = make_double2(sx, sy);
-            finish_tail(fz.rtol, fz.atol, pv[0].x, sx, ex, fe2, fy2);
-            finish_tail(fz.rtol, fz.atol, pv[0].y, sy, ey, fe2, fy2);
-          }
-        }
-        out += nx;
+    };
+    // row jl = (the row before the arriving one) goes out; frozen: it is a boundary row held at zero while t < tBoundary
+    auto emit = [&](double uN, bool frozen) {
+      double du = EXACT ? stencil_exact<MODEL>(a.k, t1, t3, cc.x, cW, cE, uS, uN)
+                        : stencil_fast<MODEL>(a.k, t1, t3, cc.x, cW, cE, uS, uN);
+      double dv = 0.0;
+      if (react_on) {
+        react<MODEL, EXACT>(a.k, __ldg(bp), cc.x, cc.y, du, dv);
+        du = frozen ? 0.0 : du;
+        dv = frozen ? 0.0 : dv;
       }
+      if (!FIN) {
+        if (active) *out = make_double2(du, dv);
+      } else {
+        // ynew = yn + sum_j hb_j F_j, err = sum_j hd_j F_j with F_{NV-1} = (du, dv): the operation order of finish_elem
+        double sx = pv[0].x, sy = pv[0].y, ex = 0.0, ey = 0.0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const double2 f = (j == NV - 1) ? make_double2(du, dv) : pv[j + 1 < NV ? j + 1 : 0];
+          sx = fma(fz.hb[j], f.x, sx); ex = fma(fz.hd[j], f.x, ex);
+          sy = fma(fz.hb[j], f.y, sy); ey = fma(fz.hd[j], f.y, ey);
+        }
+        if (active) {
+          *out = make_double2(sx, sy);
+          finish_tail(fz.rtol, fz.atol, pv[0].x, sx, ex, fe2, fy2);
+          finish_tail(fz.rtol, fz.atol, pv[0].y, sy, ey, fe2, fy2);
+        }
+      }
+      out += nx;
+      ++bp;
+    };
+    auto rotate = [&](const double2 &nn, double nW, double nE, const double2 (&v)[NV]) {
       uS = cc.x; cc = nn; cW = nW; cE = nE;
       if (FIN) {
 #pragma unroll
         for (int j = 0; j < NV; ++j) pv[j] = v[j];
       }
     };
-    for (long long j0 = jA - 1; j0 <= jB; j0 += RB, ++it) {
-      const int s = (int)(it % S);
-      mbar_wait(bars + 8u * s, (unsigned)((it / S) & 1));
-      const double2 *stage = ring + (size_t)s * RB * NV * PITCH;
-      const int nr = (jB - j0 + 1 < RB) ? (int)(jB - j0 + 1) : RB;
-      if (nr == RB) {
+    const bool ext_s = (jA == 0) && a.south != nullptr, ext_n = (jB == nyli) && a.north != nullptr;
+    const bool frz_first = react_on && a.freeze_south && jA == 0, frz_last = react_on && a.freeze_north && jB == nyli;
+    for (int j0 = jA - 1; j0 <= jB; j0 += RB) {
+      mbar_wait(bars + 8u * slot_i, slot_par);
+      const double2 *stage = ring + (size_t)slot_i * RB * NV * PITCH;
+      const int nr = (jB - j0 + 1 < RB) ? (jB - j0 + 1) : RB;
 #pragma unroll
-        for (int rr = 0; rr < RB; ++rr) step(stage + (size_t)rr * NV * PITCH, j0 + rr);
-      } else {
-        for (int rr = 0; rr < nr; ++rr) step(stage + (size_t)rr * NV * PITCH, j0 + rr);
+      for (int rr = 0; rr < RB; ++rr) {
+        if (rr < nr) {
+          const int jr = j0 + rr;
+          const double2 *slot = stage + (size_t)rr * NV * PITCH;
+          double2 nn, v[NV];
+          double nW, nE;
+          if (jr > jA + 1 && jr < jB) {          // steady state: plain row in, plain row out
+            fetch(slot, false, nn, nW, nE, v);
+            emit(nn.x, false);
+          } else {                               // the unit's first two rows and its last one
+            fetch(slot, (jr < jA && ext_s) || (jr == jB && ext_n), nn, nW, nE, v);
+            if (jr > jA) emit(nn.x, (jr == jA + 1 && frz_first) || (jr == jB && frz_last));
+          }
+          rotate(nn, nW, nE, v);
+        }
       }
       __syncwarp();   // every lane has read the stage (the values it still needs are in registers)
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8u * (S + s)) : "memory");
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8u * (S + slot_i)) : "memory");
+      if (++slot_i == S) { slot_i = 0; slot_par ^= 1u; }
     }
   }
   if (FIN) {
