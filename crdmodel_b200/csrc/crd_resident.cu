@@ -199,15 +199,6 @@ __device__ __forceinline__ void phase1(const Comb &cb, const PassCfg &c, double2
   }
 }
 
-// weighted squares of the finish with the reciprocal of the weight's denominator from rcp.approx + 3 Newton steps
-// (~1 ulp, no IEEE slow path and so no branch: the rows in flight interleave).  The sums only feed the error norm,
-// whose bits already depend on the summation order; ynew itself is formed exactly like erk_finish_kernel forms it.
-__device__ __forceinline__ void finish_tail_rcp(double rtol, double atol, double yn, double s, double err, double &e2, double &y2) {
-  const double pe = err * rcp_fast(fma(rtol, fabs(yn), atol)), py = s * rcp_fast(fma(rtol, fabs(s), atol));
-  e2 += pe * pe;
-  y2 += py * py;
-}
-
 // phase 2 over rows r = r_first + k * r_step, k = 0 .. nr-1, of the band (row k goes to row group k % G): stencil +
 // reaction with every neighbour a shared-memory read; the rows just outside the band are the neighbours' exchange
 // rows.  Writes F to `out`, or (FIN: last stage) finishes the step with the last stage's derivative still in registers

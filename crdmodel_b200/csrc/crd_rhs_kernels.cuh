@@ -533,8 +533,8 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
         }
         if (active) {
           *out = make_double2(sx, sy);
-          finish_tail(fz.rtol, fz.atol, pv[0].x, sx, ex, fe2, fy2);
-          finish_tail(fz.rtol, fz.atol, pv[0].y, sy, ey, fe2, fy2);
+          finish_tail_rcp(fz.rtol, fz.atol, pv[0].x, sx, ex, fe2, fy2);
+          finish_tail_rcp(fz.rtol, fz.atol, pv[0].y, sy, ey, fe2, fy2);
         }
       }
       out += nx;
@@ -692,9 +692,10 @@ int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
     if (a_in.nlc == 2 || a_in.nlc == 3) return launch_tile_lct<MODEL, EXACT>(g, a_in, st);
     variant = 13;
   }
-  if (variant == 21) {   // streaming kernel with 3 CTAs per SM (2 or 3 input vectors)
+  if (variant == 21) {   // streaming kernel with 3 CTAs per SM (plain state, 2 or 3 input vectors)
     if (a_in.nlc == 2) return launch_stream_nv<MODEL, EXACT, 2, false, false, 3>(g, a_in, st);
     if (a_in.nlc == 3) return launch_stream_nv<MODEL, EXACT, 3, false, false, 3>(g, a_in, st);
+    if (a_in.nlc == 0) return launch_stream_nv<MODEL, EXACT, 1, true, false, 3>(g, a_in, st);
     variant = 20;
   }
   if (variant == 20) {   // streaming kernel (persistent CTAs, shared-memory row ring)
