@@ -370,7 +370,8 @@ int launch_tile(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
 }
 
 // ---- the streaming kernel: persistent CTAs, rows flow through a shared-memory ring ------------------------
-// 2 CTAs per SM stay resident and walk over (strip of 256 columns) x (segment of rows) units.  Warp 8 is the
+// 2 or 3 CTAs per SM (MINB; the ring of the latter is smaller) stay resident and walk over (strip of 256 columns) x (segment
+// of rows) units.  Warp 8 is the
 // producer: one lane issues a 1-D TMA bulk copy per row and input vector into the next free ring slot and arms
 // that slot's "full" mbarrier with the byte count.  Warps 0..7 are consumers: a thread owns one column, waits for
 // the slot, reads (and, for a fused stage, combines sum_j c_j x_j of) its point and the two neighbours' u, releases
@@ -387,7 +388,8 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 // FIN (the last stage of an explicit RK step, NV = s vectors yn, F_0 .. F_{s-2}): the stage derivative F_{s-1} is not stored;
 // instead, while it is in registers next to the raw yn and F_j of the same point, the consumer forms ynew = yn + sum hb_j F_j
 // (written to a.ydot), err = sum hd_j F_j and the two weighted square sums of erk_finish_kernel (crd_fused.cuh arithmetic, so
-// ynew has the same bits).  Saves the finish kernel's pass over s + 1 vectors: 112 of 528 B per point and step.
+// ynew has the same bits; the weights' reciprocals are branch-free, ~1 ulp).  Saves the finish kernel's pass over s + 1 vectors:
+// 112 of 528 B per point and step.
 struct StageFin {
   double hb[kMaxLc], hd[kMaxLc];
   double rtol, atol;
