@@ -31,6 +31,27 @@ METRIC = "FHN-torus grid-point RHS evals/sec (fp64)"
 UNIT = "point-RHS/s"
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on fd 1 when NCCL_DEBUG is
+    set on the box): keep a private duplicate of fd 1 for the result and point fd 1 at stderr for everything else."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -133,7 +154,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": nranks, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(model="fhn_torus", NX=NX, budget_s=20.0):
@@ -221,6 +242,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    claim_stdout()
 
     if args.impl == "reference":
         run_reference(args, rank)
@@ -249,8 +271,6 @@ def main():
     if use_dist:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's own messages (its version banner when NCCL_DEBUG is set) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         gloo = dist.new_group(backend="gloo")
 
@@ -409,7 +429,7 @@ def main():
                 line["cpu_baseline"] = cpu_baseline(model, nx)
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % str(e)[:120]}
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     y.destroy(); ydot.destroy(); grid.close(); ctx.close()
     if use_dist:

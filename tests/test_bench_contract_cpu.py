@@ -26,3 +26,16 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_stdout_is_exactly_the_json_line_even_when_libraries_write_to_fd_1():
+    """NCCL prints its version banner on fd 1 when NCCL_DEBUG is set on the box: bench.py keeps a private duplicate of fd 1
+    for the result and sends everything else to stderr."""
+    import subprocess
+    import sys
+    code = ("import bench, os; bench.claim_stdout(); os.write(1, b'NCCL version 2.x\\n'); print('noise'); "
+            "bench.emit({'metric': 'm', 'value': 1})")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0
+    assert r.stdout == '{"metric": "m", "value": 1}\n'
+    assert "NCCL version" in r.stderr and "noise" in r.stderr
