@@ -13,6 +13,7 @@
  *               out[0] = sum_global (err_i  * w_i )^2,  w_i  = 1/(rtol |yn_i|   + atol)
  *               out[1] = sum_global (ynew_i * w'_i)^2,  w'_i = 1/(rtol |ynew_i| + atol)
  *               (the error weights are a pure function of the state, so no ewt vector is stored).
+ *   rhs_lincomb_finish  the LAST stage evaluation and erk_finish in one pass (the stage derivative is never stored)
  *   erk_evolve  the whole adaptive step loop (stages, finish, error test, step controller) inside ONE persistent
  *               cooperative kernel: no launch and no host round trip per step.  For the meshes that live in L2
  *               (the reference's default 400 x 1600 / 100 x 400 grids) a step is bound by launch latency, not by
