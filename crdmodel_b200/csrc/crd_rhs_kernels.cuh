@@ -377,6 +377,12 @@ int launch_tile(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
 // the slot, reads (and, for a fused stage, combines sum_j c_j x_j of) its point and the two neighbours' u, releases
 // the slot on the "empty" mbarrier, and with the previous two rows still in registers computes the row before.
 // Every state row is fetched once (plus one halo row per segment end); no CTA start-up per tile.
+// a shared-memory load the compiler may not merge with an earlier load of the same address (FIN 2 reads a slot twice on purpose)
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   unsigned ok = 0;
   while (!ok) {
@@ -396,7 +402,10 @@ struct StageFin {
   double *partial;   // [2][kRedBlocks] per-CTA sums
 };
 
-template <int MODEL, bool EXACT, int NV, bool PLAIN, int RB, bool FIN, int MINB = 2>
+// FIN = 2: the same arithmetic with a smaller register footprint (fits 3 CTAs per SM): instead of the raw vectors of the row
+// that goes out next, a thread carries yn and the partial sums yn + sum_{j<NV-1} hb_j F_j, sum_{j<NV-1} hd_j F_j (same operation
+// order, the last term is added when F_{NV-1} exists), formed from a second read of the ring slot after the row before has gone out.
+template <int MODEL, bool EXACT, int NV, bool PLAIN, int RB, int FIN, int MINB = 2>
 __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, int seg_rows, int S, const StageFin fz) {
   constexpr int TX = 256, PITCH = TX + 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -489,7 +498,8 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
     const double *bp = a.brow + jA;   // beta of the next row to go out
     double uS = 0.0, cW = 0.0, cE = 0.0;
     double2 cc = make_double2(0.0, 0.0);
-    double2 pv[FIN ? NV : 1] = {};   // FIN: the raw vectors (yn, F_0 ..) of the row that goes out next
+    double2 pv[FIN == 1 ? NV : 1] = {};   // FIN 1: the raw vectors (yn, F_0 ..) of the row that goes out next (FIN 2: yn)
+    double2 psum = make_double2(0.0, 0.0), perr = make_double2(0.0, 0.0);   // FIN 2: the partial sums of that row
     // the arriving row: nn (combined centre), nW / nE (combined u of the neighbours), v (raw vectors, FIN)
     auto fetch = [&](const double2 *slot, bool ext, double2 &nn, double &nW, double &nE, double2 (&v)[NV]) {
       if (PLAIN || ext) {
@@ -522,8 +532,16 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
         du = frozen ? 0.0 : du;
         dv = frozen ? 0.0 : dv;
       }
-      if (!FIN) {
+      if constexpr (!FIN) {
         if (active) *out = make_double2(du, dv);
+      } else if constexpr (FIN == 2) {
+        const double sx = fma(fz.hb[NV - 1], du, psum.x), ex = fma(fz.hd[NV - 1], du, perr.x);
+        const double sy = fma(fz.hb[NV - 1], dv, psum.y), ey = fma(fz.hd[NV - 1], dv, perr.y);
+        if (active) {
+          *out = make_double2(sx, sy);
+          finish_tail_rcp(fz.rtol, fz.atol, pv[0].x, sx, ex, fe2, fy2);
+          finish_tail_rcp(fz.rtol, fz.atol, pv[0].y, sy, ey, fe2, fy2);
+        }
       } else {
         // ynew = yn + sum_j hb_j F_j, err = sum_j hd_j F_j with F_{NV-1} = (du, dv): the operation order of finish_elem
         double sx = pv[0].x, sy = pv[0].y, ex = 0.0, ey = 0.0;
@@ -542,11 +560,23 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
       out += nx;
       ++bp;
     };
-    auto rotate = [&](const double2 &nn, double nW, double nE, const double2 (&v)[NV]) {
+    auto rotate = [&](const double2 &nn, double nW, double nE, const double2 (&v)[NV], const double2 *slot, bool ext) {
       uS = cc.x; cc = nn; cW = nW; cE = nE;
-      if (FIN) {
+      if constexpr (FIN == 1) {
 #pragma unroll
         for (int j = 0; j < NV; ++j) pv[j] = v[j];
+      } else if constexpr (FIN == 2) {
+        if (!ext) {   // (a ghost row never goes out)
+          const unsigned sa = smem_u32(slot + c + 1);
+          pv[0] = lds_f64x2(sa);
+          psum = pv[0]; perr = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int j = 0; j < NV - 1; ++j) {
+            const double2 f = lds_f64x2(sa + (unsigned)((j + 1) * PITCH * 16));
+            psum.x = fma(fz.hb[j], f.x, psum.x); perr.x = fma(fz.hd[j], f.x, perr.x);
+            psum.y = fma(fz.hb[j], f.y, psum.y); perr.y = fma(fz.hd[j], f.y, perr.y);
+          }
+        }
       }
     };
     const bool ext_s = (jA == 0) && a.south != nullptr, ext_n = (jB == nyli) && a.north != nullptr;
@@ -565,11 +595,13 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
           if (jr > jA + 1 && jr < jB) {          // steady state: plain row in, plain row out
             fetch(slot, false, nn, nW, nE, v);
             emit(nn.x, false);
+            rotate(nn, nW, nE, v, slot, false);
           } else {                               // the unit's first two rows and its last one
-            fetch(slot, (jr < jA && ext_s) || (jr == jB && ext_n), nn, nW, nE, v);
+            const bool ext = (jr < jA && ext_s) || (jr == jB && ext_n);
+            fetch(slot, ext, nn, nW, nE, v);
             if (jr > jA) emit(nn.x, (jr == jA + 1 && frz_first) || (jr == jB && frz_last));
+            rotate(nn, nW, nE, v, slot, ext);
           }
-          rotate(nn, nW, nE, v);
         }
       }
       __syncwarp();   // every lane has read the stage (the values it still needs are in registers)
@@ -617,7 +649,7 @@ __global__ void __launch_bounds__(256) fin_reduce_kernel(const double *partial, 
 }
 
 // MINB = CTAs per SM: 2 (ring of ~100 KB, up to 113 registers) or 3 (ring of ~66 KB, up to 75 registers: 24 consumer warps per SM)
-template <int MODEL, bool EXACT, int NV, bool PLAIN, bool FIN = false, int MINB = 2>
+template <int MODEL, bool EXACT, int NV, bool PLAIN, int FIN = 0, int MINB = 2>
 int launch_stream_nv(crd_grid *g, const RhsArgs &a, cudaStream_t st, const StageFin *fin = nullptr, int *nblocks = nullptr) {
   constexpr int RB = (NV == 1) ? 4 : (NV <= 3 ? 2 : 1);   // rows per ring stage
   const int seg_rows = 128;
@@ -660,7 +692,11 @@ int launch_stream(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
 int launch_stage_finish(crd_grid *g, const RhsArgs &a, const StageFin &fin, cudaStream_t st, int *nblocks) {
   if (a.nlc != 5) return 1;
   const bool exact = g->p.arith == CRD_ARITH_EXACT;
-#define CRD_FIN(M) (exact ? launch_stream_nv<M, true, 5, false, true>(g, a, st, &fin, nblocks) : launch_stream_nv<M, false, 5, false, true>(g, a, st, &fin, nblocks))
+  // default (and grid variant 22): the partial-sum form of the finish (FIN 2) with 3 CTAs per SM, 24 consumer warps: 4.58 vs
+  // 4.90 ms at 16384^2 (EXACT; FAST 4.16 vs 4.79), same bits.  Variant 23: FIN 2 with 2 CTAs per SM; 24: FIN 1 (the raw vectors
+  // in registers) with 2 CTAs per SM, the former default.  profiles/README.md
+#define CRD_FIN_(M, F, B) (exact ? launch_stream_nv<M, true, 5, false, F, B>(g, a, st, &fin, nblocks) : launch_stream_nv<M, false, 5, false, F, B>(g, a, st, &fin, nblocks))
+#define CRD_FIN(M) (g->variant == 24 ? CRD_FIN_(M, 1, 2) : g->variant == 23 ? CRD_FIN_(M, 2, 2) : CRD_FIN_(M, 2, 3))
   switch (g->p.model) {
     case CRD_FHN_TORUS: return CRD_FIN(CRD_FHN_TORUS);
     case CRD_GOLDBETER_TORUS: return CRD_FIN(CRD_GOLDBETER_TORUS);
@@ -668,6 +704,7 @@ int launch_stage_finish(crd_grid *g, const RhsArgs &a, const StageFin &fin, cuda
     case CRD_GOLDBETER_FLAT: return CRD_FIN(CRD_GOLDBETER_FLAT);
   }
 #undef CRD_FIN
+#undef CRD_FIN_
   return 1;
 }
 

@@ -252,14 +252,20 @@ def test_last_stage_fused_with_the_finish_equals_stage_then_finish(crd, ctx, mod
     hd = [h * (1 / 6 + 0.5), h * (1 / 3 - 7 / 3), h * (1 / 3 - 7 / 3), h * (1 / 6 - 13 / 6), h * 16 / 3]
     rtol, atol = 1e-5, 1e-10
     for t in (10.0, 50.0):
-        F5, want, got = grid.new_vector(), grid.new_vector(), grid.new_vector()
+        F5, want = grid.new_vector(), grid.new_vector()
         grid.f_lincomb(t, c, X, F5)
         e2, y2 = crd.N_VErkFinish(hb, hd, X[0], X[1:] + [F5], want, rtol, atol)
-        rc, fe2, fy2 = grid.f_lincomb_finish(t, c, hb, hd, X, got, rtol, atol)
-        assert rc == 0
-        assert got.to_numpy().tobytes() == want.to_numpy().tobytes()
-        assert abs(fe2 - e2) <= 1e-11 * e2 and abs(fy2 - y2) <= 1e-11 * y2
-        for v in (F5, want, got):
+        # 0: the default (partial sums carried per thread, 3 CTAs per SM); 23: the same with 2 CTAs per SM; 24: raw vectors in registers
+        for variant in (0, 23, 24):
+            got = grid.new_vector()
+            grid.set_variant(variant)
+            rc, fe2, fy2 = grid.f_lincomb_finish(t, c, hb, hd, X, got, rtol, atol)
+            grid.set_variant(0)
+            assert rc == 0, variant
+            assert got.to_numpy().tobytes() == want.to_numpy().tobytes(), variant
+            assert abs(fe2 - e2) <= 1e-11 * e2 and abs(fy2 - y2) <= 1e-11 * y2, variant
+            got.destroy()
+        for v in (F5, want):
             v.destroy()
     # does not apply: small meshes (the caller issues the two operations)
     small = crd.Grid(ctx, crd.make_params(model, 64, 96, arith=ar))
