@@ -220,6 +220,45 @@ def default_mesh_integrations(crd, ctx):
     return out
 
 
+def stage_kernel_times(crd, ctx, grid, y, ydot, model, nx, nyl, reps=20):
+    """The kernels a step of the explicit 5-stage method issues on a mesh beyond L2, besides the plain f(tn, yn) of the headline:
+    the 2-vector stage f(yn + c F) (three per step) and the last stage fused with the step finish (yn, F1..F4 in; ynew out, F5
+    never stored).  Algorithmic bytes: 16 B per point and vector read or written."""
+    h = 1e-3
+    c5 = [1.0, h * 5 / 32, h * 7 / 32, h * 13 / 32, -h / 32]
+    hb = [h / 6, h / 3, h / 3, h / 6, 0.0]
+    hd = [h * (1 / 6 + 0.5), h * (1 / 3 - 7 / 3), h * (1 / 3 - 7 / 3), h * (1 / 6 - 13 / 6), h * 16 / 3]
+    X = [y]
+    try:
+        for j in range(1, 5):
+            v = grid.new_vector()
+            X.append(v)
+            grid.fill_synthetic(v, seed=0x5EED + j)
+            crd.N_VScale(0.25, v, v)
+        out = []
+        points = nx * nyl
+        for name, nvec, call in (
+                ("stage f(yn + c*F): rhs_stream_kernel<NV=2>, 3 CTAs/SM", 3, lambda: grid.f_lincomb(T_EVAL, [1.0, 0.5 * h], X[:2], ydot)),
+                ("last stage + finish: rhs_stream_kernel<NV=5, FIN>, 3 CTAs/SM", 6,
+                 lambda: grid.f_lincomb_finish(T_EVAL, c5, hb, hd, X, ydot, 1e-5, 1e-10))):
+            rc = None
+            for _ in range(3):
+                rc = call()
+            if isinstance(rc, tuple) and rc[0] != 0:      # the fused finish does not apply to this mesh (small slab)
+                out.append({"kernel": name, "skipped": "does not apply to this mesh"})
+                continue
+            ctx.sync(); ctx.timer_start()
+            for _ in range(reps):
+                call()
+            ms = ctx.timer_stop() / reps
+            out.append({"kernel": name, "ms": ms, "algorithmic_bytes": 16 * nvec * points, "GBs": 16 * nvec * points / ms / 1e6,
+                        "launches_timed": reps, "note": "CUDA events around %d consecutive calls (the fused finish returns its two sums to the host: one stream synchronisation per call is inside)" % reps})
+        return out
+    finally:
+        for v in X[1:]:
+            v.destroy()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -394,9 +433,21 @@ def main():
         except Exception as e:
             integ_small = {"error": str(e)[:200]}
 
+    # ---- the other kernels of one large-mesh integrator step, each timed alone (CUDA events, back-to-back launches) ----
+    stage_kernels = None
+    if not args.no_integrator and world == 1:
+        try:
+            stage_kernels = stage_kernel_times(crd, ctx, grid, y, ydot, model, nx, nyl)
+        except Exception as e:
+            stage_kernels = {"error": str(e)[:200]}
+
     if rank == 0:
         peaks, peaks_src = measured_peaks()
         achieved = BYTES_PER_POINT * points / (ms_per_step * 1e-3) / 1e9
+        if isinstance(stage_kernels, list):
+            for k in stage_kernels:
+                if "GBs" in k:
+                    k["frac_of_hbm_peak"] = k["GBs"] / peaks["hbm_gbs"]
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -422,7 +473,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                         "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
                         "matches_device_result": e2e_ok, "api": "crd_rhs_host (C ABI, pinned host buffers, chunked 3-stream pipeline)"},
-                "gpu_launches": int(launches), "clocks": clocks, "integrator": integ, "integrator_default_meshes": integ_small}
+                "gpu_launches": int(launches), "clocks": clocks, "integrator": integ, "integrator_stage_kernels": stage_kernels,
+                "integrator_default_meshes": integ_small}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 os.sched_setaffinity(0, all_cpus)
