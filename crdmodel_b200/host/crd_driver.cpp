@@ -15,8 +15,8 @@
 // System.fused (1), System.reuseFirstStage (= fused), System.resident (1), Parameters.phiMesh, Parameters.Zs / Ys.
 #include <pthread.h>
 #include <sys/mman.h>
-#include <sys/wait.h>
 #include <unistd.h>
+
 
 #include <cmath>
 #include <cstdio>
@@ -29,6 +29,7 @@
 
 #include "crd_b200.h"
 #include "crd_ini.hpp"
+#include "crd_workers.hpp"
 #include "crd_writer.hpp"
 
 #ifndef CRD_DRIVER_MODEL
@@ -421,19 +422,5 @@ int main(int argc, char *argv[]) {
   pthread_barrierattr_setpshared(&ba, PTHREAD_PROCESS_SHARED);
   pthread_barrier_init(&g_shm->bar, &ba, nranks);
   g_shm->failed = 0;
-  std::vector<pid_t> kids;
-  for (int r = 1; r < nranks; ++r) {
-    fflush(NULL);
-    pid_t pid = fork();
-    if (pid < 0) { perror("fork"); return 1; }
-    if (pid == 0) _exit(run(c, r, nranks));
-    kids.push_back(pid);
-  }
-  int rc = run(c, 0, nranks);
-  for (pid_t k : kids) {
-    int st = 0;
-    waitpid(k, &st, 0);
-    if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) rc = rc ? rc : 1;
-  }
-  return rc;
+  return crd::run_ranks(nranks, [&](int r) { return run(c, r, nranks); });
 }
