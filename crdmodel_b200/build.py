@@ -60,7 +60,7 @@ def build_drivers(verbose=False):
     os.makedirs(os.path.join(ROOT, "bin"), exist_ok=True)
     for name, model in (("FHNmodel_torus", 0), ("GoldbeterModel_torus", 1), ("FHNmodel_flat", 2), ("GoldbeterModel_flat", 3)):
         exe = os.path.join(ROOT, "bin", name)
-        deps = [src, LIB] + [os.path.join(HERE, "host", h) for h in ("crd_ini.hpp", "crd_writer.hpp", "crd_workers.hpp")]
+        deps = [src, LIB] + [os.path.join(HERE, "host", h) for h in ("crd_ini.hpp", "crd_writer.hpp", "crd_workers.hpp", "crd_steady.hpp")]
         if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(d) for d in deps):
             out.append(exe)
             continue

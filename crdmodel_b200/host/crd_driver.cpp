@@ -12,7 +12,8 @@
 // Ranks are GPUs: `System.gpus = G` (or CRD_GPUS=G) forks G worker processes, one per GPU, each owning a
 // phi slab; neighbours' boundary rows travel through CUDA-IPC peer mappings, norms through shared memory.
 // New optional keys (absent => the reference's behaviour): System.gpus, System.arith (exact|fast),
-// System.fused (1), System.reuseFirstStage (= fused), System.resident (1), Parameters.phiMesh, Parameters.Zs / Ys.
+// System.fused (1), System.reuseFirstStage (= fused), System.resident (1), Parameters.phiMesh, Parameters.Zs / Ys,
+// System.steadyStateCommand (the reference's SolveGoldbeterODE.py protocol instead of the closed-form steady state).
 #include <pthread.h>
 #include <sys/mman.h>
 #include <unistd.h>
@@ -29,6 +30,7 @@
 
 #include "crd_b200.h"
 #include "crd_ini.hpp"
+#include "crd_steady.hpp"
 #include "crd_workers.hpp"
 #include "crd_writer.hpp"
 
@@ -101,24 +103,6 @@ int shm_allreduce(double *vals, int n, int op, void *) {
   return 0;
 }
 
-// Goldbeter steady state for spatially constant beta.  The reference integrates the two ODEs with an external
-// script (GoldbeterModel_torus.cpp:254-261, util/GoldbeterModel/SolveGoldbeterODE.py); the fixed point itself
-// is Zs = (v0 + v1 beta)/k (sum of the two equations) and Ys the root of v2(Zs) - v3(Zs, Y) - kf Y = 0.
-void goldbeter_steady_state(double beta, double &Zs, double &Ys) {
-  const double v0 = 1.0, k = 10.0, kf = 1.0, v1 = 7.3, VM2 = 65.0, VM3 = 500.0, K2 = 1.0, KR = 2.0, KA = 0.9;
-  Zs = (v0 + v1 * beta) / k;
-  const double z2 = Zs * Zs, z4 = z2 * z2;
-  const double v2 = VM2 * z2 / (K2 * K2 + z2);
-  auto g = [&](double Y) { return v2 - VM3 * Y * Y * z4 / ((KR * KR + Y * Y) * (KA * KA * KA * KA + z4)) - kf * Y; };
-  double lo = 0.0, hi = 1.0;
-  while (g(hi) > 0.0 && hi < 1e6) hi *= 2.0;
-  for (int it = 0; it < 200; ++it) {
-    const double mid = 0.5 * (lo + hi);
-    if (g(mid) > 0.0) lo = mid; else hi = mid;
-  }
-  Ys = 0.5 * (lo + hi);
-}
-
 struct Config {
   double DIFF, BETA, SURFACE_LENGTH, SURFACE_WIDTH, WAVE_LENGTH, WAVE_WIDTH, T_BOUNDARY, T_FINAL, BETA_MIN = 0, BETA_MAX = 0;
   int WAVE_INSIDE = 0, OUTPUT_TIMESTEP, NX, INCLUDE_ALL_VARS, VARY_BETA, JUST_DIFFUSION = 0, IC_TYPE = 0;
@@ -178,8 +162,15 @@ Config read_config(const char *path) {
   if (!kFhn) {
     if (pt.has("Parameters.Zs") && pt.has("Parameters.Ys")) {
       c.Zs = pt.get<double>("Parameters.Zs"); c.Ys = pt.get<double>("Parameters.Ys"); c.have_zs = true;
+    } else if (pt.has("System.steadyStateCommand")) {
+      // the reference's protocol (GoldbeterModel_torus.cpp:254-261): `<command> <beta>` prints "[Zs] [Ys]"
+      const std::string cmd = pt.str("System.steadyStateCommand");
+      if (!crd::goldbeter_steady_state_from_command(cmd, pt.str("Parameters.beta"), c.Zs, c.Ys)) {
+        cerr << "steady state: `" << cmd << " " << pt.str("Parameters.beta") << "` did not print \"[Zs] [Ys]\"; using the closed form\n";
+        crd::goldbeter_steady_state(c.BETA, c.Zs, c.Ys);
+      }
     } else {
-      goldbeter_steady_state(c.BETA, c.Zs, c.Ys);
+      crd::goldbeter_steady_state(c.BETA, c.Zs, c.Ys);
     }
   }
   return c;
