@@ -170,6 +170,7 @@ SIGNATURES = {
     "crd_ARKodeSetStageFinish": (I, [P, I]),
     "crd_ARKodeSetInitStep": (I, [P, D]),
     "crd_ARKodeSetFixedStep": (I, [P, D]),
+    "crd_ARKodeGetButcherTable": (I, [P, P, P, P, c_double_p, c_double_p, c_double_p, c_double_p]),
 }
 
 _lib = None

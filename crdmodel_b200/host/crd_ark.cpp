@@ -475,6 +475,19 @@ int crd_ARKodeSetFixedStep(void *mem, realtype hfixed) {
   return ARK_SUCCESS;
 }
 
+int crd_ARKodeGetButcherTable(void *mem, int *s, int *q, int *p, realtype *A, realtype *c, realtype *b, realtype *b2) {
+  static_assert(S_MAX == CRD_ARK_TABLE_DIM, "table dimension");
+  if (!mem) return ARK_MEM_NULL;
+  if (!s || !q || !p || !A || !c || !b || !b2) return ARK_ILL_INPUT;
+  const ArkMem *m = (const ArkMem *)mem;
+  *s = m->s; *q = m->q; *p = m->p;
+  for (int i = 0; i < S_MAX; ++i) {
+    for (int j = 0; j < S_MAX; ++j) A[i * S_MAX + j] = m->A[i][j];
+    c[i] = m->c[i]; b[i] = m->b[i]; b2[i] = m->b2[i];
+  }
+  return ARK_SUCCESS;
+}
+
 int ARKode(void *mem, realtype tout, N_Vector yout, realtype *tret, int itask) {
   if (!mem) return ARK_MEM_NULL;
   ArkMem *m = (ArkMem *)mem;

@@ -95,6 +95,11 @@ int crd_ARKodeSetStageFinish(void *arkode_mem, int on);
 int crd_ARKodeSetInitStep(void *arkode_mem, realtype hin);
 /* Fixed step size (no error test, no adaptivity); 0 switches adaptivity back on. */
 int crd_ARKodeSetFixedStep(void *arkode_mem, realtype hfixed);
+/* The explicit method in use (what ARKode 1.x reports through ARKodeGetCurrentButcherTables): s stages, order q, embedding
+ * order p; A is filled row-major with CRD_ARK_TABLE_DIM columns ([CRD_ARK_TABLE_DIM * CRD_ARK_TABLE_DIM] doubles), c, b and the
+ * embedding weights b2 with CRD_ARK_TABLE_DIM entries each. */
+#define CRD_ARK_TABLE_DIM 8
+int crd_ARKodeGetButcherTable(void *arkode_mem, int *s, int *q, int *p, realtype *A, realtype *c, realtype *b, realtype *b2);
 
 #ifdef __cplusplus
 }

@@ -81,6 +81,31 @@ def test_harmonic_oscillator_tolerance_and_dense_output(K):
     assert st2["nst"] == st["nst"] and st2["nfe"] < st["nfe"]
 
 
+def test_butcher_table_satisfies_the_order_conditions(K):
+    """The method restated from ARKode 1.x's documentation (Zonneveld 5-3-4; SUNDIALS itself is not available here): the
+    weights b must satisfy all eight conditions of order 4, the embedding b2 the four of order 3 (and NOT those of order 4, or the
+    difference would not estimate the error), c must be the row sums of a strictly lower-triangular A."""
+    K.crd_ARKodeGetButcherTable.argtypes = [P_] + [C.POINTER(C.c_int)] * 3 + [C.POINTER(D_)] * 4
+    mem = P_(K.ARKodeCreate())
+    s, q, p = C.c_int(), C.c_int(), C.c_int()
+    A, c, b, b2 = (D_ * 64)(), (D_ * 8)(), (D_ * 8)(), (D_ * 8)()
+    assert K.crd_ARKodeGetButcherTable(mem, C.byref(s), C.byref(q), C.byref(p), A, c, b, b2) == 0
+    K.ARKodeFree(C.byref(mem))
+    assert (s.value, q.value, p.value) == (5, 4, 3)
+    n = s.value
+    A = np.array(A[:]).reshape(8, 8)[:n, :n]
+    c, b, b2 = np.array(c[:n]), np.array(b[:n]), np.array(b2[:n])
+    assert np.all(np.triu(A) == 0.0)                      # explicit
+    assert np.allclose(A.sum(1), c, atol=1e-15)
+
+    def conditions(w):
+        return [w.sum() - 1, w @ c - 1 / 2, w @ c ** 2 - 1 / 3, w @ (A @ c) - 1 / 6,                       # orders 1-3
+                w @ c ** 3 - 1 / 4, (w * c) @ (A @ c) - 1 / 8, w @ (A @ c ** 2) - 1 / 12, w @ (A @ (A @ c)) - 1 / 24]   # order 4
+    assert np.max(np.abs(conditions(b))) < 1e-15
+    e = np.abs(conditions(b2))
+    assert np.max(e[:4]) < 1e-14 and np.max(e[4:]) > 1e-3
+
+
 def test_fourth_order_convergence_fixed_step(K):
     f = make_rhs(K, lambda t, y: np.array([y[1], -y[0]]))
     errs = []
