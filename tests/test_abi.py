@@ -72,3 +72,28 @@ def test_decomp_phi_matches_reference_formula(crd):
                 assert js == ny * r // nr and je == ny * (r + 1) // nr - 1
                 rows += list(range(js, je + 1))
             assert rows == list(range(ny))
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: every public header must compile as C99 (cgo / JNI / ctypes generators include it as C) and
+    as C++11, on its own, and a C program using the structs must link against the library."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    for h in ("crd_b200.h", "crd_ark.h", "crd_sundials_compat.h"):
+        for lang, std in (("c", "-std=c99"), ("c++", "-std=c++11")):
+            r = subprocess.run(["gcc", "-x", lang, std, "-pedantic", "-Wall", "-Werror", "-I" + inc, "-fsyntax-only", "-"],
+                               input='#include "%s"\n' % h, capture_output=True, text=True)
+            assert r.returncode == 0, (h, lang, r.stderr)
+    from crdmodel_b200 import build as B
+    B.build()
+    src = tmp_path / "use.c"
+    src.write_text('#include <stdio.h>\n#include "crd_b200.h"\n#include "crd_ark.h"\n'
+                   'int main(void) { int64_t js, je; crd_params p; p.nx = 4; (void)p;\n'
+                   '  if (crd_decomp_phi(10, 2, 1, &js, &je) != 0 || js != 5 || je != 9) return 1;\n'
+                   '  void *m = ARKodeCreate(); if (!m) return 2; ARKodeFree(&m);\n'
+                   '  printf("%d\\n", crd_device_count()); return 0; }\n')
+    exe = tmp_path / "use"
+    subprocess.run(["gcc", "-std=c99", "-I" + inc, str(src), "-o", str(exe), "-L" + B.LIB_DIR, "-lcrd_b200",
+                    "-Wl,-rpath," + B.LIB_DIR], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
