@@ -122,3 +122,19 @@ def test_torus_operator_second_order(oracle):
         exact = -m * m / (R + r * np.cos(th))[None, :] ** 2 * np.cos(m * ph)[:, None]
         errs.append(np.abs(d[2:-2] - exact[2:-2]).max())   # away from the (n-1)-spacing seam
     assert errs[1] < errs[0] / 3.0
+
+
+def test_restatement_matches_reference_digests_at_baseline_meshes(oracle):
+    """BASELINE configs[0..2] mesh sizes: the checker against SHA-256 digests / sampled values of the reference's own f()
+    (tests/golden/rhs_baseline_digests.json, generated from oracle/_ref by tests/golden/make_baseline_digests.py)."""
+    import hashlib
+    import json
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rhs_baseline_digests.json")))
+    assert len(cases) >= 6
+    for c in cases:
+        nx, ny = c["nx"], c["ny"]
+        y = oracle.fill_state(c["model"], 2 * nx * ny, seed=c["seed"])
+        got = oracle.rhs(oracle.make_params(c["model"], nx, ny, just_diffusion=c["just_diffusion"], t_boundary=38.0), c["t"], y)
+        assert hashlib.sha256(got.tobytes()).hexdigest() == c["sha256"], c["name"]      # same libm here: bit for bit, pow included
+        for i, hx in c["samples"].items():
+            assert got[int(i)] == float.fromhex(hx)

@@ -110,3 +110,22 @@ def test_exact_division_edge_values_on_the_host(harness, oracle):
             with np.errstate(all="ignore"):
                 got = host_rhs(harness, P, 50.0, y)
             assert got.tobytes() == ref.tobytes(), (model, mag)
+
+
+def test_device_point_source_at_baseline_meshes(harness, oracle):
+    """BASELINE configs[0..2] mesh sizes against the digests of the reference's own f() (tests/golden/rhs_baseline_digests.json)."""
+    import hashlib
+    import json
+    import crdmodel_b200.api as api
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "rhs_baseline_digests.json")))
+    for c in cases:
+        nx, ny = c["nx"], c["ny"]
+        y = oracle.fill_state(c["model"], 2 * nx * ny, seed=c["seed"])
+        P = api.make_params(c["model"], nx, ny, just_diffusion=c["just_diffusion"], t_boundary=38.0)
+        got = host_rhs(harness, P, c["t"], y)
+        if c["model"].startswith("fhn") or c["just_diffusion"] == 1:
+            assert hashlib.sha256(got.tobytes()).hexdigest() == c["sha256"], c["name"]
+        else:
+            sc = scale_of(P, y)
+            for i, hx in c["samples"].items():
+                assert abs(got[int(i)] - float.fromhex(hx)) <= 4e-16 * sc[int(i)], (c["name"], i)

@@ -60,6 +60,27 @@ def test_golden_vectors(crd, ctx, oracle):
         assert np.all(np.abs(fast - ref) <= 1e-12 * scale_of(oracle, P, y)), ("fast", k, np.abs(fast - ref).max())
 
 
+def test_baseline_mesh_digests(crd, ctx, oracle):
+    """BASELINE configs[0..2] mesh sizes against digests of the reference's own f() (tests/golden/rhs_baseline_digests.json,
+    generated from oracle/_ref by make_baseline_digests.py): SHA-256 of the ydot bytes where the path is bit-exact (FHN flat /
+    torus, diffusion-only Goldbeter), sampled values within 4e-16 of the summed terms for the Goldbeter kinetics."""
+    import hashlib
+    import json
+    cases = json.load(open(os.path.join(os.path.dirname(GOLDEN), "rhs_baseline_digests.json")))
+    assert len(cases) >= 6
+    for c in cases:
+        nx, ny = c["nx"], c["ny"]
+        y = oracle.fill_state(c["model"], 2 * nx * ny, seed=c["seed"])
+        kw = dict(just_diffusion=c["just_diffusion"], t_boundary=38.0)
+        got = gpu_rhs(crd, ctx, c["model"], nx, ny, c["t"], y, crd.ARITH_EXACT, **kw)
+        if c["model"].startswith("fhn") or c["just_diffusion"] == 1:
+            assert hashlib.sha256(got.tobytes()).hexdigest() == c["sha256"], c["name"]
+        else:
+            sc = scale_of(oracle, oracle.make_params(c["model"], nx, ny, **kw), y)
+            for i, hx in c["samples"].items():
+                assert abs(got[int(i)] - float.fromhex(hx)) <= 4e-16 * sc[int(i)], (c["name"], i)
+
+
 @pytest.mark.parametrize("model", MODELS)
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 10, 11, 12, 13, 14, 15, 16, 17, 20])
 def test_parity_vs_oracle(crd, ctx, oracle, model, variant):
