@@ -33,7 +33,10 @@
 #define G_n 2.0
 #define G_p 4.0
 
-int crd_oracle_rhs_rows(const crd_oracle_params *P, double t, const double *y, double *out, long j0, long j1) {
+/* rows [j0, j1) of the global mesh.  yoff = 0: y is the whole global state.  yoff = j0 - 1 (band form): y holds only the
+ * rows j0-1 .. j1 (periodic in the global mesh), i.e. row j of the mesh is row j - yoff of y with the wrapped neighbours of
+ * row 0 / ny-1 stored where the band has them (first / last row of y). */
+static int rhs_rows_impl(const crd_oracle_params *P, double t, const double *y, double *out, long j0, long j1, int band) {
   const long nx = P->nx, ny = P->ny;
   const int torus = (P->model == CRD_ORACLE_FHN_TORUS || P->model == CRD_ORACLE_GOLDBETER_TORUS);
   const int fhn = (P->model == CRD_ORACLE_FHN_TORUS || P->model == CRD_ORACLE_FHN_FLAT);
@@ -55,7 +58,8 @@ int crd_oracle_rhs_rows(const crd_oracle_params *P, double t, const double *y, d
   const int react = fhn || P->just_diffusion == 0;          /* GoldbeterModel_torus.cpp:668 */
 
   for (long j = j0; j < j1; ++j) {
-    const long jS = (j == 0) ? ny - 1 : j - 1, jN = (j == ny - 1) ? 0 : j + 1;
+    long jS = (j == 0) ? ny - 1 : j - 1, jN = (j == ny - 1) ? 0 : j + 1, jC = j;
+    if (band) { jC = j - j0 + 1; jS = jC - 1; jN = jC + 1; }
     const double yy = YMIN + (j) * (dy);                    /* :623 (js = 0) */
     double b = P->beta;
     if (fhn) { if (P->vary_beta != 0) b = P->beta_min + yy * (P->beta_max - P->beta_min) / (YMAX - YMIN); } /* :625-632 */
@@ -64,8 +68,8 @@ int crd_oracle_rhs_rows(const crd_oracle_params *P, double t, const double *y, d
     const int frozen = react && t < P->t_boundary && (j == ny - 1 || j == 0);
     for (long i = 0; i < nx; ++i) {
       const long iW = (i == 0) ? nx - 1 : i - 1, iE = (i == nx - 1) ? 0 : i + 1;
-      const double uC = y[2 * (i + j * nx)], vC = y[2 * (i + j * nx) + 1];
-      const double uW = y[2 * (iW + j * nx)], uE = y[2 * (iE + j * nx)];
+      const double uC = y[2 * (i + jC * nx)], vC = y[2 * (i + jC * nx) + 1];
+      const double uW = y[2 * (iW + jC * nx)], uE = y[2 * (iE + jC * nx)];
       const double uS = y[2 * (i + jS * nx)], uN = y[2 * (i + jN * nx)];
       double du, dv = 0.0;                                  /* N_VConst(0.0, ydot) :506 */
       if (torus) {
@@ -94,6 +98,15 @@ int crd_oracle_rhs_rows(const crd_oracle_params *P, double t, const double *y, d
     }
   }
   return 0;
+}
+
+int crd_oracle_rhs_rows(const crd_oracle_params *P, double t, const double *y, double *out, long j0, long j1) {
+  return rhs_rows_impl(P, t, y, out, j0, j1, 0);
+}
+
+/* band form (what one rank of a phi split computes): yband = rows j0-1 .. j0+nrows of the global mesh (nrows + 2 rows) */
+int crd_oracle_rhs_band(const crd_oracle_params *P, double t, long j0, long nrows, const double *yband, double *out) {
+  return rhs_rows_impl(P, t, yband, out, j0, j0 + nrows, 1);
 }
 
 int crd_oracle_rhs(const crd_oracle_params *P, double t, const double *y, double *ydot) {

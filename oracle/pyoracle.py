@@ -51,6 +51,7 @@ def lib():
         L = C.CDLL(path)
         L.crd_oracle_rhs.argtypes = [C.POINTER(OracleParams), C.c_double, _dp, _dp]
         L.crd_oracle_rhs_rows.argtypes = [C.POINTER(OracleParams), C.c_double, _dp, _dp, C.c_long, C.c_long]
+        L.crd_oracle_rhs_band.argtypes = [C.POINTER(OracleParams), C.c_double, C.c_long, C.c_long, _dp, _dp]
         L.crd_oracle_fill_state.argtypes = [C.c_int, C.c_ulonglong, C.c_long, C.c_long, _dp]
         L.crd_oracle_fill_state.restype = None
         _lib = L
@@ -83,6 +84,27 @@ def fill_state(model, n_elems, seed=0x5EED, first_elem=0):
     return out
 
 
+def band_state(model, nx, ny, j0, nrows, seed=0x5EED):
+    """Rows j0-1 .. j0+nrows (nrows + 2 rows, periodic in the global mesh) of the synthetic global state [ny][nx][2]."""
+    out = np.empty((nrows + 2, 2 * nx))
+    lo, hi = j0 - 1, j0 + nrows
+    if lo >= 0 and hi < ny:
+        return fill_state(model, 2 * nx * (nrows + 2), seed, 2 * nx * lo).reshape(nrows + 2, 2 * nx)
+    for r, j in enumerate(range(lo, hi + 1)):
+        out[r] = fill_state(model, 2 * nx, seed, 2 * nx * (j % ny))
+    return out
+
+
+def rhs_band(P, t, j0, nrows, yband):
+    """Plain-C restatement on a band of phi rows of the global mesh (what one rank of a phi split computes)."""
+    yband = np.ascontiguousarray(yband, dtype=np.float64)
+    out = np.empty(nrows * P.nx * 2)
+    rc = lib().crd_oracle_rhs_band(C.byref(P), float(t), j0, nrows, _ptr(yband), _ptr(out))
+    if rc != 0:
+        raise RuntimeError("crd_oracle_rhs_band failed: %d" % rc)
+    return out
+
+
 _ref = {}
 
 
@@ -97,6 +119,7 @@ def ref_lib(model):
     if name not in _ref:
         L = C.CDLL(os.path.join(HERE, "_ref", "libcrd_ref_%s.so" % name))
         L.crd_ref_rhs.argtypes = [C.POINTER(OracleParams), C.c_int, C.c_double, _dp, _dp, C.c_int, _dp]
+        L.crd_ref_rhs_band.argtypes = [C.POINTER(OracleParams), C.c_double, C.c_long, C.c_long, _dp, _dp]
         L.crd_ref_decomp.argtypes = [C.POINTER(OracleParams), C.c_int, C.c_int, C.POINTER(C.c_long)]
         L.crd_ref_main.argtypes = [C.c_char_p, C.c_int]
         _ref[name] = L
@@ -113,6 +136,16 @@ def ref_rhs(P, t, y, nranks=1, reps=1, want_out=True):
     if rc != 0:
         raise RuntimeError("reference f() returned %d" % rc)
     return out, sec.value
+
+
+def ref_rhs_band(P, t, j0, nrows, yband):
+    """The reference's own f() (Exchange included) on the band of global phi rows [j0, j0+nrows); yband as band_state gives it."""
+    yband = np.ascontiguousarray(yband, dtype=np.float64)
+    out = np.empty(nrows * P.nx * 2)
+    rc = ref_lib(P.model).crd_ref_rhs_band(C.byref(P), float(t), j0, nrows, _ptr(yband), _ptr(out))
+    if rc != 0:
+        raise RuntimeError("reference f() on a band returned %d" % rc)
+    return out
 
 
 def ref_decomp(P, nranks, rank):

@@ -158,6 +158,33 @@ int crd_ref_rhs(const crd_oracle_params *P, int nranks, double t, const double *
   return flag;
 }
 
+// The reference's f() on a band of phi rows of a larger global mesh (what one rank of a 1-D phi split computes): UserData as
+// main() + SetupDecomp() fill it for one rank, then js / je / nyl set to the band; the rows outside the band come from the
+// caller through the shim's S / N receives.  Exchange(), the stencil, the frozen-row and beta(phi) logic run unmodified.
+int crd_ref_rhs_band(const crd_oracle_params *P, double t, long j0, long nrows, const double *yband, double *out) {
+  if (nrows < 2 || j0 < 0 || j0 + nrows > P->ny) return -2;   // the reference's face / corner code needs nyl >= 2
+  set_globals(P);
+  crdshim_mpi_set_world(1);
+  crdshim_mpi_bind(0);
+  UserData *udata = new UserData;
+  int flag = fill_udata(udata, P, 0);   // buffers sized for the whole mesh: large enough for any band
+  if (flag != 0) { delete udata; return flag; }
+  udata->js = j0; udata->je = j0 + nrows - 1; udata->nyl = nrows;
+  const long nx = udata->nx, N = 2 * nx * nrows;
+  N_Vector y = N_VNew_Parallel(udata->comm, N, 2 * nx * udata->ny);
+  N_Vector ydot = N_VNew_Parallel(udata->comm, N, 2 * nx * udata->ny);
+  std::memcpy(NV_DATA_P(y), yband + 2 * nx, sizeof(double) * N);
+  crdshim_mpi_band_halo(yband, yband + 2 * nx * (nrows + 1));
+  flag = f(t, y, ydot, (void *)udata);
+  crdshim_mpi_band_halo(nullptr, nullptr);
+  std::memcpy(out, NV_DATA_P(ydot), sizeof(double) * N);
+  N_VDestroy_Parallel(y);
+  N_VDestroy_Parallel(ydot);
+  REF_FREE(udata);
+  delete udata;
+  return flag;
+}
+
 // The reference's extents for rank `rank` of `nranks` (SetupDecomp): out = {is, ie, js, je, nxl, nyl, dims0, dims1}
 int crd_ref_decomp(const crd_oracle_params *P, int nranks, int rank, long out[8]) {
   set_globals(P);

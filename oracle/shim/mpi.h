@@ -48,6 +48,8 @@ int MPI_Barrier(MPI_Comm comm);
 /* shim control (not MPI): world size for subsequent runs; per-thread rank binding */
 void crdshim_mpi_set_world(int nranks);
 void crdshim_mpi_bind(int rank);
+/* band mode (world size 1): Exchange()'s S / N receives deliver these rows instead of the rank's own (NULL = off) */
+void crdshim_mpi_band_halo(const double *south_row, const double *north_row);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,8 @@ struct World {
 } W;
 
 thread_local int tl_rank = 0;
+// band mode (single rank): rows a neighbouring rank would have sent (see crdshim_mpi_band_halo)
+thread_local const double *tl_halo_s = nullptr, *tl_halo_n = nullptr;
 
 size_t dt_size(MPI_Datatype dt) {
   switch (dt) {
@@ -55,6 +57,13 @@ void crdshim_mpi_set_world(int nranks) {
 }
 
 void crdshim_mpi_bind(int rank) { tl_rank = rank; }
+
+// Band mode, world size 1: the calling thread runs the reference's f() on a band of phi rows [js, je] of a larger
+// global mesh.  Its Exchange() posts four receives per call in the order W, E, S, N (FHNmodel_torus.cpp:825-846)
+// and, alone in the world, would receive its own rows back (periodic self-exchange).  With this set, the S and N
+// receives (the 3rd and 4th of each group) deliver the caller's rows js-1 and je+1 instead -- what the neighbouring
+// ranks of a phi split would have sent.  NULL, NULL switches it off.
+void crdshim_mpi_band_halo(const double *south_row, const double *north_row) { tl_halo_s = south_row; tl_halo_n = north_row; }
 
 int MPI_Init(int *, char ***) { return MPI_SUCCESS; }
 int MPI_Finalize(void) { return MPI_SUCCESS; }
@@ -145,6 +154,8 @@ int MPI_Wait(MPI_Request *req, MPI_Status *) {
   size_t n = m.bytes.size() < (size_t)req->count ? m.bytes.size() : (size_t)req->count;
   std::memcpy(req->buf, m.bytes.data(), n);
   q.erase(req->seq);
+  if (tl_halo_s && req->seq % 4 == 2) std::memcpy(req->buf, tl_halo_s, (size_t)req->count);
+  if (tl_halo_n && req->seq % 4 == 3) std::memcpy(req->buf, tl_halo_n, (size_t)req->count);
   return MPI_SUCCESS;
 }
 

@@ -125,16 +125,46 @@ def test_torus_operator_second_order(oracle):
 
 
 def test_restatement_matches_reference_digests_at_baseline_meshes(oracle):
-    """BASELINE configs[0..2] mesh sizes: the checker against SHA-256 digests / sampled values of the reference's own f()
-    (tests/golden/rhs_baseline_digests.json, generated from oracle/_ref by tests/golden/make_baseline_digests.py)."""
+    """BASELINE configs[0..4] mesh sizes: the checker against SHA-256 digests / sampled values of the reference's own f()
+    (tests/golden/rhs_baseline_digests.json + rhs_baseline_samples.npz, generated from oracle/_ref by
+    tests/golden/make_baseline_digests.py).  The two headline meshes (2.7e8 points, ~10-30 s of one core each) are checked
+    through their sampled values: the row of each of 48 samples is recomputed in band form."""
     import hashlib
     import json
-    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rhs_baseline_digests.json")))
-    assert len(cases) >= 6
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    cases = json.load(open(os.path.join(here, "rhs_baseline_digests.json")))
+    samples = np.load(os.path.join(here, "rhs_baseline_samples.npz"))
+    assert len(cases) >= 13
     for c in cases:
         nx, ny = c["nx"], c["ny"]
+        if "sample_set" in c:
+            P = oracle.make_params(c["model"], nx, ny, just_diffusion=c["just_diffusion"], t_boundary=38.0)
+            el, val = samples["idx_" + c["sample_set"]], samples["val_" + c["sample_set"]]
+            pick = np.concatenate([np.arange(0, 8), np.arange(len(el) - 8, len(el)), np.linspace(8, len(el) - 9, 32).astype(int)])
+            for k in pick:
+                j, off = divmod(int(el[k]), 2 * nx)
+                row = oracle.rhs_band(P, c["t"], j, 1, oracle.band_state(c["model"], nx, ny, j, 1, seed=c["seed"]))
+                assert row[off] == val[k], (c["name"], k)
+            continue
         y = oracle.fill_state(c["model"], 2 * nx * ny, seed=c["seed"])
         got = oracle.rhs(oracle.make_params(c["model"], nx, ny, just_diffusion=c["just_diffusion"], t_boundary=38.0), c["t"], y)
         assert hashlib.sha256(got.tobytes()).hexdigest() == c["sha256"], c["name"]      # same libm here: bit for bit, pow included
         for i, hx in c["samples"].items():
             assert got[int(i)] == float.fromhex(hx)
+
+
+def test_band_form_equals_the_whole_mesh(oracle):
+    """crd_oracle_rhs_band / crd_ref_rhs_band (the reference's f() and Exchange() on the rows one rank of a phi split owns, the
+    neighbours' rows delivered as messages) reproduce the same rows of the np = 1 result bit for bit: bands at the global
+    boundary rows (frozen while t < tBoundary, periodic wrap), in the interior, and the whole mesh."""
+    nx, ny = 37, 29
+    for model in ("fhn_torus", "gb_torus", "fhn_flat", "gb_flat"):
+        P = oracle.make_params(model, nx, ny, t_boundary=38.0)
+        y = oracle.fill_state(model, 2 * nx * ny)
+        for t in (10.0, 50.0):
+            ref = oracle.rhs(P, t, y).reshape(ny, 2 * nx)
+            for j0, n in ((0, 2), (0, 3), (5, 4), (ny - 2, 2), (ny - 3, 3), (0, ny), (4, 1), (0, 1), (ny - 1, 1)):
+                yb = oracle.band_state(model, nx, ny, j0, n)
+                assert oracle.rhs_band(P, t, j0, n, yb).tobytes() == ref[j0:j0 + n].tobytes(), (model, t, j0, n)
+                if n >= 2 and oracle.ref_available(model):      # the reference's face / corner code needs two rows
+                    assert oracle.ref_rhs_band(P, t, j0, n, yb).tobytes() == ref[j0:j0 + n].tobytes(), (model, t, j0, n)
