@@ -49,6 +49,9 @@ SIGNATURES = {
     "crd_ctx_stream": (P, [P]),
     "crd_ctx_device": (I, [P]),
     "crd_ctx_sync": (I, [P]),
+    "crd_ctx_set_halo_timeout": (I, [P, D]),
+    "crd_ctx_failed": (I, [P]),
+    "crd_ctx_clear_error": (I, [P]),
     "crd_ctx_launch_count": (C.c_int64, [P]),
     "crd_timer_start": (I, [P]),
     "crd_timer_stop": (I, [P, c_double_p]),
@@ -89,6 +92,11 @@ SIGNATURES = {
     "crd_grid_resident_cycles": (I, [P, C.POINTER(C.c_int64)]),
     "crd_fill_synthetic": (I, [P, I, C.c_uint64, C.c_int64, C.c_int64, P]),
     "crd_fill_initial_conditions": (I, [P, C.POINTER(IcParams), P]),
+    "crd_snapshot_create": (P, [P, C.c_int64, I, I]),
+    "crd_snapshot_destroy": (None, [P]),
+    "crd_snapshot_begin": (I, [P, P]),
+    "crd_snapshot_wait": (I, [P, I, C.POINTER(P), C.POINTER(P)]),
+    "crd_snapshot_release": (I, [P, I]),
     # device N_Vector
     "N_VNew_Crd": (P, [P, L, L]),
     "N_VNewEmpty_Crd": (P, [P, L, L]),
@@ -125,8 +133,12 @@ SIGNATURES = {
     "N_VMinQuotient_Crd": (D, [P, P]),
     "N_VLinearCombination_Crd": (I, [I, c_double_p, C.POINTER(P), P]),
     "N_VErkFinish_Crd": (I, [I, c_double_p, c_double_p, P, C.POINTER(P), P, D, D, c_double_p]),
+    "N_VErkFinishSeq_Crd": (I, [I, c_double_p, c_double_p, P, C.POINTER(P), P, D, D, c_double_p]),
     "crd_nv_fused_ops": (C.POINTER(FusedOps), []),
     "crd_nv_fused_vector_ops": (C.POINTER(FusedOps), []),
+    "crd_nv_fused_ops_exact": (C.POINTER(FusedOps), []),
+    "crd_nv_fused_vector_ops_exact": (C.POINTER(FusedOps), []),
+    "crd_nv_fused_ops_for": (C.POINTER(FusedOps), [P]),
     # generic dispatchers + ARKode-legacy interface (crd_sundials_compat.h, crd_ark.h)
     "N_VClone": (P, [P]),
     "N_VDestroy": (None, [P]),

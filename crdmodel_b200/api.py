@@ -72,6 +72,18 @@ class Context:
     def sync(self):
         check(lib().crd_ctx_sync(self._h), "crd_ctx_sync")
 
+    def set_halo_timeout(self, milliseconds):
+        """How long a phi-split evaluation waits for a neighbour's boundary rows before the context fails."""
+        check(lib().crd_ctx_set_halo_timeout(self._h, float(milliseconds)), "crd_ctx_set_halo_timeout")
+
+    @property
+    def failed(self):
+        """0, or the device's error code once a halo wait has timed out (every call then fails until clear_error)."""
+        return lib().crd_ctx_failed(self._h)
+
+    def clear_error(self):
+        check(lib().crd_ctx_clear_error(self._h), "crd_ctx_clear_error")
+
     @property
     def launches(self):
         return lib().crd_ctx_launch_count(self._h)
@@ -189,11 +201,13 @@ def N_VLinearCombination(c, X, z):
     check(lib().N_VLinearCombination_Crd(n, cc, xx, _h(z)), "N_VLinearCombination_Crd")
 
 
-def N_VErkFinish(hb, hd, yn, F, ynew, rtol, atol):
+def N_VErkFinish(hb, hd, yn, F, ynew, rtol, atol, exact=False):
+    """exact: the bits of the op-by-op sequence (N_VErkFinishSeq_Crd) instead of fused multiply-adds."""
     s = len(hb)
     out = (C.c_double * 2)()
-    check(lib().N_VErkFinish_Crd(s, (C.c_double * s)(*hb), (C.c_double * s)(*hd), _h(yn),
-                                 (C.c_void_p * s)(*[_h(f) for f in F]), _h(ynew), rtol, atol, out), "N_VErkFinish_Crd")
+    fn = lib().N_VErkFinishSeq_Crd if exact else lib().N_VErkFinish_Crd
+    check(fn(s, (C.c_double * s)(*hb), (C.c_double * s)(*hd), _h(yn),
+             (C.c_void_p * s)(*[_h(f) for f in F]), _h(ynew), rtol, atol, out), "N_VErkFinish_Crd")
     return out[0], out[1]
 
 
@@ -314,9 +328,14 @@ class ARKodeSolver:
         check(L.ARKodeSetUserData(self.mem, grid.handle), "ARKodeSetUserData")
         check(L.ARKodeSetMaxNumSteps(self.mem, max_steps), "ARKodeSetMaxNumSteps")
         # fused: True / "full" = fused vector ops + stage assembly inside the RHS; "ops" = fused vector ops only;
-        # False = the op-by-op SUNDIALS 2.x sequence
+        # False = the op-by-op SUNDIALS 2.x sequence.  The table follows the grid's arithmetic: on an EXACT grid every fused
+        # entry reproduces the bits of the op-by-op sequence (crd_nv_fused_ops_exact), on a FAST grid they are fma chains.
         if fused:
-            table = L.crd_nv_fused_vector_ops() if fused == "ops" else L.crd_nv_fused_ops()
+            exact = grid.params.arith == ARITH_EXACT
+            if fused == "ops":
+                table = L.crd_nv_fused_vector_ops_exact() if exact else L.crd_nv_fused_vector_ops()
+            else:
+                table = L.crd_nv_fused_ops_for(grid.handle)
             check(L.crd_ARKodeSetFusedOps(self.mem, C.cast(table, C.c_void_p)), "crd_ARKodeSetFusedOps")
         # stage 1 of every step is f(tn, yn), which the previous step has just evaluated for its dense output: with the
         # fused operations it is reused by default (bit-identical results, 5 instead of 6 evaluations per step); the

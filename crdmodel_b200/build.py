@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libcrd_b200.so")
 
-CUDA_SOURCES = ["csrc/crd_ctx.cu", "csrc/crd_rhs.cu", "csrc/crd_nvector.cu", "csrc/crd_resident.cu"]
+CUDA_SOURCES = ["csrc/crd_ctx.cu", "csrc/crd_rhs.cu", "csrc/crd_nvector.cu", "csrc/crd_resident.cu", "csrc/crd_snapshot.cu"]
 HOST_SOURCES = ["host/crd_ark.cpp", "host/crd_nvector_generic.c"]
 HEADERS = ["csrc/crd_common.cuh", "csrc/crd_grid.cuh", "csrc/crd_rhs_kernels.cuh", "csrc/crd_rhs_point.cuh", "csrc/crd_fused.cuh", "csrc/crd_tables.hpp", "../include/crd_b200.h", "../include/crd_ark.h",
            "../include/crd_sundials_compat.h"]

@@ -1,5 +1,8 @@
 // crd_ctx.cu — device context, memory helpers, timers, synthetic-state generator.
+#include <cstdlib>
+
 #include "crd_common.cuh"
+#include "crd_fused.cuh"
 
 namespace crd {
 static thread_local char g_err[512] = "";
@@ -8,6 +11,20 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof g_err, fmt, ap);
   va_end(ap);
+}
+int allreduce_dd(crd_ctx *c, double &hi, double &lo, double *plain) {
+  if (c->nranks <= 1) return 0;
+  if (c->nranks > kMaxRanks || !c->allreduce) { set_error("allreduce_dd: %d ranks without a usable allreduce hook", c->nranks); return -1; }
+  double v[3 * kMaxRanks];
+  const int n = 3 * c->nranks;
+  for (int i = 0; i < n; ++i) v[i] = 0.0;
+  v[3 * c->rank] = hi; v[3 * c->rank + 1] = lo; v[3 * c->rank + 2] = plain ? *plain : 0.0;
+  if (c->allreduce(v, n, CRD_SUM, c->allreduce_user) != 0) { set_error("allreduce hook failed"); return -1; }
+  double h = v[0], l = v[1], p = v[2];
+  for (int r = 1; r < c->nranks; ++r) { dd_merge(h, l, v[3 * r], v[3 * r + 1]); p += v[3 * r + 2]; }
+  hi = h; lo = l;
+  if (plain) *plain = p;
+  return 0;
 }
 }  // namespace crd
 
@@ -38,8 +55,17 @@ crd_ctx *crd_ctx_create(int device, void *stream) {
     set_error("device %d is sm_%d%d; libcrd_b200 is built for sm_100a only", device, prop.major, prop.minor);
     return nullptr;
   }
+  if (prop.multiProcessorCount * 3 > kRedBlocks) {
+    set_error("device %d has %d SMs; the per-launch partial-sum tables are sized for %d (B200)", device, prop.multiProcessorCount, crd::kSMs);
+    return nullptr;
+  }
   crd_ctx *c = new crd_ctx;
   c->device = device;
+  c->sms = prop.multiProcessorCount;
+  if (const char *e = std::getenv("CRD_HALO_TIMEOUT_MS")) {
+    const long long ms = std::atoll(e);
+    if (ms > 0) c->halo_timeout_ns = ms * 1000000LL;
+  }
   if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
   else { CRD_CUDA_NULL(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   CRD_CUDA_NULL(cudaMalloc(&c->red_partial, sizeof(double) * kRedSlots * kRedBlocks));
@@ -82,9 +108,26 @@ int crd_ctx_device(crd_ctx *c) { return c ? c->device : -1; }
 int64_t crd_ctx_launch_count(crd_ctx *c) { return c ? c->launches : 0; }
 
 int crd_ctx_sync(crd_ctx *c) {
+  if (!c) return -1;
+  if (device_failed(c)) return -2;
   if (use(c)) return -1;
-  CRD_CUDA(cudaStreamSynchronize(c->stream));
-  if (*c->err_host != 0) { set_error("device-side error %d (halo wait timed out)", *c->err_host); return -2; }
+  return sync_stream(c, "crd_ctx_sync") ? -2 : 0;
+}
+
+int crd_ctx_set_halo_timeout(crd_ctx *c, double milliseconds) {
+  if (!c || !(milliseconds > 0.0)) { set_error("crd_ctx_set_halo_timeout: bad arguments"); return -1; }
+  c->halo_timeout_ns = (long long)(milliseconds * 1.0e6);
+  return 0;
+}
+
+int crd_ctx_failed(crd_ctx *c) { return c ? (device_failed(c) ? *c->err_host : 0) : -1; }
+
+int crd_ctx_clear_error(crd_ctx *c) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  *c->err_host = 0;
+  c->failed = false;
   return 0;
 }
 
@@ -124,14 +167,12 @@ int crd_free_host(void *p) { CRD_CUDA(cudaFreeHost(p)); return 0; }
 int crd_memcpy_h2d(crd_ctx *c, void *dst, const void *src, size_t bytes) {
   if (use(c)) return -1;
   CRD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
-  CRD_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  return sync_stream(c, "crd_memcpy_h2d");
 }
 int crd_memcpy_d2h(crd_ctx *c, void *dst, const void *src, size_t bytes) {
   if (use(c)) return -1;
   CRD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
-  CRD_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  return sync_stream(c, "crd_memcpy_d2h");
 }
 int crd_memset_zero(crd_ctx *c, void *dst, size_t bytes) {
   if (use(c)) return -1;

@@ -33,9 +33,9 @@ inline double *D(N_Vector v) { return NVC(v)->data; }
 inline long long LEN(N_Vector v) { return NVC(v)->local_length; }
 inline crd_ctx *CTX(N_Vector v) { return NVC(v)->ctx; }
 
-inline unsigned int grid_for(long long n_items) {
+inline unsigned int grid_for(long long n_items, int sms = crd::kSMs) {
   long long b = (n_items + 255) / 256;
-  const long long cap = (long long)kSMs * 16;
+  const long long cap = (long long)sms * 16;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (unsigned int)b;
@@ -69,7 +69,7 @@ template <class F, bool HAS_X, bool HAS_Y>
 void ew(crd_ctx *c, F f, const double *x, const double *y, double *z, long long n, const char *name) {
   if (n <= 0) return;
   if (use(c)) return;
-  ew_kernel<F, HAS_X, HAS_Y><<<grid_for((n + 1) / 2), 256, 0, c->stream>>>(f, x, y, z, n);
+  ew_kernel<F, HAS_X, HAS_Y><<<grid_for((n + 1) / 2, c->sms), 256, 0, c->stream>>>(f, x, y, z, n);
   check_launch(c, name);
 }
 
@@ -148,6 +148,81 @@ __device__ __forceinline__ void block_finish(double (&acc)[NV], double *partial,
   }
 }
 
+// ---- order-independent sums of squares: double-double accumulation (crd_fused.cuh) -------------------------------------
+// partial layout [3][kRedBlocks]: hi | plain second value | lo; result[0] = hi, result[1] = plain, result[2] = lo
+template <bool HAS_PLAIN>
+__device__ __forceinline__ void block_finish_dd(double hi, double lo, double pl, double *partial, unsigned int *ticket, double *result) {
+  __shared__ double sm[3][kRedThreads / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dd_shfl_down(hi, lo, o);
+    if (HAS_PLAIN) pl += __shfl_down_sync(0xffffffffu, pl, o);
+  }
+  if (lane == 0) { sm[0][wid] = hi; sm[1][wid] = pl; sm[2][wid] = lo; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double h = sm[0][0], p = sm[1][0], l = sm[2][0];
+    for (int w = 1; w < kRedThreads / 32; ++w) { dd_merge(h, l, sm[0][w], sm[2][w]); p += sm[1][w]; }
+    partial[blockIdx.x] = h; partial[kRedBlocks + blockIdx.x] = p; partial[2 * kRedBlocks + blockIdx.x] = l;
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  double h = 0.0, l = 0.0, p = 0.0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += kRedThreads) {
+    dd_merge(h, l, __ldcg(&partial[b]), __ldcg(&partial[2 * kRedBlocks + b]));
+    p += __ldcg(&partial[kRedBlocks + b]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dd_shfl_down(h, l, o);
+    p += __shfl_down_sync(0xffffffffu, p, o);
+  }
+  if (lane == 0) { sm[0][wid] = h; sm[1][wid] = p; sm[2][wid] = l; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    h = sm[0][0]; p = sm[1][0]; l = sm[2][0];
+    for (int w = 1; w < kRedThreads / 32; ++w) { dd_merge(h, l, sm[0][w], sm[2][w]); p += sm[1][w]; }
+    result[0] = h; result[1] = p; result[2] = l;   // mapped pinned host memory
+    *ticket = 0;
+    __threadfence_system();
+  }
+}
+
+// sum_i RN(RN(x_i w_i)^2) [over id_i > 0]: every term rounded like nvector_parallel's loop, the sum in double-double
+template <bool HAS_Z>
+__global__ void __launch_bounds__(kRedThreads) red_sqw_kernel(const double *x, const double *w, const double *z, long long n,
+                                                              double *partial, unsigned int *ticket, double *result) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  double hi = 0.0, lo = 0.0;
+  auto term = [&](double xv, double wv, double zv) {
+    const double p = __dmul_rn(xv, wv);
+    if (!HAS_Z || zv > 0.0) dd_add(hi, lo, __dmul_rn(p, p));
+  };
+  const bool aligned = (((uintptr_t)x | (uintptr_t)w | (uintptr_t)z) & 15) == 0;
+  if (aligned) {
+    const long long n2 = n >> 1;
+    const double2 *x2 = reinterpret_cast<const double2 *>(x), *w2 = reinterpret_cast<const double2 *>(w);
+    const double2 *z2 = reinterpret_cast<const double2 *>(z);
+#pragma unroll 4
+    for (long long i = tid; i < n2; i += stride) {
+      const double2 a = x2[i], b = w2[i];
+      const double2 c = HAS_Z ? z2[i] : make_double2(0, 0);
+      term(a.x, b.x, c.x);
+      term(a.y, b.y, c.y);
+    }
+    if (tid == 0 && (n & 1)) term(x[n - 1], w[n - 1], HAS_Z ? z[n - 1] : 0.0);
+  } else {
+    for (long long i = tid; i < n; i += stride) term(x[i], w[i], HAS_Z ? z[i] : 0.0);
+  }
+  block_finish_dd<false>(hi, lo, 0.0, partial, ticket, result);
+}
+
 // M: functor  double operator()(double x, double y, double z)
 template <int OP, class M, bool HAS_Y, bool HAS_Z>
 __global__ void __launch_bounds__(kRedThreads) red_kernel(M m, const double *x, const double *y, const double *z, long long n,
@@ -179,8 +254,6 @@ __global__ void __launch_bounds__(kRedThreads) red_kernel(M m, const double *x, 
 struct MDot { __device__ double operator()(double x, double y, double) const { return x * y; } };
 struct MAbs { __device__ double operator()(double x, double, double) const { return fabs(x); } };
 struct MId { __device__ double operator()(double x, double, double) const { return x; } };
-struct MSqW { __device__ double operator()(double x, double w, double) const { double p = x * w; return p * p; } };
-struct MSqWMask { __device__ double operator()(double x, double w, double id) const { double p = x * w; return id > 0.0 ? p * p : 0.0; } };
 struct MQuot { __device__ double operator()(double n, double d, double) const { return d == 0.0 ? DBL_MAX : __ddiv_rn(n, d); } };
 
 // local reduction -> host value -> cross-rank allreduce hook
@@ -189,11 +262,11 @@ double reduce(crd_ctx *c, M m, const double *x, const double *y, const double *z
   double v = OP == OP_SUM ? 0.0 : (OP == OP_MAX ? -DBL_MAX : DBL_MAX);
   if (use(c)) return NAN;
   if (n > 0) {
-    unsigned int blocks = grid_for((n + 1) / 2);
+    unsigned int blocks = grid_for((n + 1) / 2, c->sms);
     if (blocks > (unsigned)kRedBlocks) blocks = kRedBlocks;
     red_kernel<OP, M, HAS_Y, HAS_Z><<<blocks, kRedThreads, 0, c->stream>>>(m, x, y, z, n, c->red_partial, c->red_ticket, c->red_result_dev);
     if (check_launch(c, name)) return NAN;
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { set_error("%s: stream synchronize failed", name); return NAN; }
+    if (sync_stream(c, name)) return NAN;
     v = c->red_result_host[0];
   }
   if (c->nranks > 1) {
@@ -201,6 +274,23 @@ double reduce(crd_ctx *c, M m, const double *x, const double *y, const double *z
     if (c->allreduce(&v, 1, op, c->allreduce_user) != 0) { set_error("%s: allreduce hook failed", name); return NAN; }
   }
   return v;
+}
+
+// sum of weighted squares, order-independent: local double-double -> ranks' pairs merged in rank order -> one rounding
+template <bool HAS_Z>
+double reduce_sqw(crd_ctx *c, const double *x, const double *w, const double *z, long long n, const char *name) {
+  double hi = 0.0, lo = 0.0;
+  if (use(c)) return NAN;
+  if (n > 0) {
+    unsigned int blocks = grid_for((n + 1) / 2, c->sms);
+    if (blocks > (unsigned)kRedBlocks) blocks = kRedBlocks;
+    red_sqw_kernel<HAS_Z><<<blocks, kRedThreads, 0, c->stream>>>(x, w, z, n, c->red_partial, c->red_ticket, c->red_result_dev);
+    if (check_launch(c, name)) return NAN;
+    if (sync_stream(c, name)) return NAN;
+    hi = c->red_result_host[0]; lo = c->red_result_host[2];
+  }
+  if (allreduce_dd(c, hi, lo, nullptr)) return NAN;
+  return hi + lo;
 }
 
 // ---- flag-producing element-wise ops (invtest, constrmask): write z and reduce a MIN flag ---------------
@@ -241,7 +331,7 @@ double flag_op(crd_ctx *c, F f, const double *x, const double *y, double *z, lon
     if (blocks > (unsigned)kRedBlocks) blocks = kRedBlocks;
     flag_kernel<F><<<blocks, kRedThreads, 0, c->stream>>>(f, x, y, z, n, c->red_partial, c->red_ticket, c->red_result_dev);
     if (check_launch(c, name)) return NAN;
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { set_error("%s: stream synchronize failed", name); return NAN; }
+    if (sync_stream(c, name)) return NAN;
     v = c->red_result_host[0];
   }
   if (c->nranks > 1 && c->allreduce(&v, 1, CRD_MIN, c->allreduce_user) != 0) { set_error("%s: allreduce hook failed", name); return NAN; }
@@ -275,13 +365,14 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LinCombArgs a, doubl
 }
 
 // ---- fused: ynew = yn + sum hb_j F_j ; err = sum hd_j F_j ; two weighted square sums (crd_fused.cuh) ----------
-template <int S>
+// SEQ: the bits of the op-by-op sequence (separately rounded chains, IEEE weights, double-double error sum)
+template <int S, bool SEQ>
 __global__ void __launch_bounds__(kRedThreads) erk_finish_kernel(const FinishArgs a, long long n, double *partial,
                                                                  unsigned int *ticket, double *result) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long n2 = n >> 1;
-  double acc[2] = {0.0, 0.0};
+  FinAcc<SEQ> acc;
   double2 *o2 = reinterpret_cast<double2 *>(a.ynew);
   for (long long i = tid; i < n2; i += stride) {
     double2 f2[S];
@@ -292,18 +383,18 @@ __global__ void __launch_bounds__(kRedThreads) erk_finish_kernel(const FinishArg
 #pragma unroll
     for (int j = 0; j < S; ++j) { fx[j] = f2[j].x; fy[j] = f2[j].y; }
     double2 o;
-    finish_elem<S>(a, y0.x, fx, o.x, acc[0], acc[1]);
-    finish_elem<S>(a, y0.y, fy, o.y, acc[0], acc[1]);
+    finish_elem<SEQ, S>(a, y0.x, fx, o.x, acc);
+    finish_elem<SEQ, S>(a, y0.y, fy, o.y, acc);
     o2[i] = o;
   }
   if (tid == 0 && (n & 1)) {
     double f[S];
     for (int j = 0; j < S; ++j) f[j] = a.F[j][n - 1];
     double o;
-    finish_elem<S>(a, a.yn[n - 1], f, o, acc[0], acc[1]);
+    finish_elem<SEQ, S>(a, a.yn[n - 1], f, o, acc);
     a.ynew[n - 1] = o;
   }
-  block_finish<OP_SUM, 2>(acc, partial, ticket, result);
+  block_finish_dd<true>(acc.e_hi, acc.e_lo, acc.y2, partial, ticket, result);
 }
 
 struct _generic_N_Vector_Ops g_ops = {
@@ -315,8 +406,13 @@ struct _generic_N_Vector_Ops g_ops = {
     N_VDotProd_Crd, N_VMaxNorm_Crd, N_VWrmsNorm_Crd, N_VWrmsNormMask_Crd, N_VMin_Crd, N_VWL2Norm_Crd, N_VL1Norm_Crd,
     N_VCompare_Crd, N_VInvTest_Crd, N_VConstrMask_Crd, N_VMinQuotient_Crd};
 
+// FAST grids: chains of fused multiply-adds.  EXACT grids: every fused entry reproduces the bits of the op-by-op sequence
+// (crd_fused.cuh); there is no fused lincomb in that table, so the rare combinations outside a step (dense output) are issued
+// op by op as well.
 const crd_fused_ops g_fused = {N_VLinearCombination_Crd, N_VErkFinish_Crd, crd_f_lincomb, crd_erk_evolve, crd_f_lincomb_finish};
 const crd_fused_ops g_fused_ops_only = {N_VLinearCombination_Crd, N_VErkFinish_Crd, nullptr, nullptr, nullptr};
+const crd_fused_ops g_fused_exact = {nullptr, N_VErkFinishSeq_Crd, crd_f_lincomb, crd_erk_evolve, crd_f_lincomb_finish};
+const crd_fused_ops g_fused_exact_ops_only = {nullptr, N_VErkFinishSeq_Crd, nullptr, nullptr, nullptr};
 
 }  // namespace
 
@@ -439,16 +535,16 @@ realtype N_VMaxNorm_Crd(N_Vector x) {
   return v < 0.0 ? 0.0 : v;
 }
 realtype N_VWrmsNorm_Crd(N_Vector x, N_Vector w) {
-  double s = reduce<OP_SUM, MSqW, true, false>(CTX(x), MSqW{}, D(x), D(w), nullptr, LEN(x), "nv_wrmsnorm");
+  double s = reduce_sqw<false>(CTX(x), D(x), D(w), nullptr, LEN(x), "nv_wrmsnorm");
   return std::sqrt(s / (double)NVC(x)->global_length);
 }
 realtype N_VWrmsNormMask_Crd(N_Vector x, N_Vector w, N_Vector id) {
-  double s = reduce<OP_SUM, MSqWMask, true, true>(CTX(x), MSqWMask{}, D(x), D(w), D(id), LEN(x), "nv_wrmsnormmask");
+  double s = reduce_sqw<true>(CTX(x), D(x), D(w), D(id), LEN(x), "nv_wrmsnormmask");
   return std::sqrt(s / (double)NVC(x)->global_length);
 }
 realtype N_VMin_Crd(N_Vector x) { return reduce<OP_MIN, MId, false, false>(CTX(x), MId{}, D(x), nullptr, nullptr, LEN(x), "nv_min"); }
 realtype N_VWL2Norm_Crd(N_Vector x, N_Vector w) {
-  return std::sqrt(reduce<OP_SUM, MSqW, true, false>(CTX(x), MSqW{}, D(x), D(w), nullptr, LEN(x), "nv_wl2norm"));
+  return std::sqrt(reduce_sqw<false>(CTX(x), D(x), D(w), nullptr, LEN(x), "nv_wl2norm"));
 }
 realtype N_VL1Norm_Crd(N_Vector x) { return reduce<OP_SUM, MAbs, false, false>(CTX(x), MAbs{}, D(x), nullptr, nullptr, LEN(x), "nv_l1norm"); }
 realtype N_VMinQuotient_Crd(N_Vector num, N_Vector denom) {
@@ -474,7 +570,7 @@ int N_VLinearCombination_Crd(int n, const realtype *cf, N_Vector *X, N_Vector z)
     if ((uintptr_t)a.x[j] & 15) { set_error("N_VLinearCombination_Crd: vectors must be 16-byte aligned"); return -1; }
   }
   if ((uintptr_t)D(z) & 15) { set_error("N_VLinearCombination_Crd: vectors must be 16-byte aligned"); return -1; }
-  const unsigned int blocks = grid_for((len + 1) / 2);
+  const unsigned int blocks = grid_for((len + 1) / 2, c->sms);
   double *zd = D(z);
   switch (n) {
     case 1: lincomb_kernel<1><<<blocks, 256, 0, c->stream>>>(a, zd, len); break;
@@ -489,13 +585,13 @@ int N_VLinearCombination_Crd(int n, const realtype *cf, N_Vector *X, N_Vector z)
   return check_launch(c, "lincomb_kernel");
 }
 
-int N_VErkFinish_Crd(int s, const realtype *hb, const realtype *hd, N_Vector yn, N_Vector *F, N_Vector ynew,
-                     realtype rtol, realtype atol, realtype out[2]) {
+static int erk_finish_impl(bool seq, int s, const realtype *hb, const realtype *hd, N_Vector yn, N_Vector *F, N_Vector ynew,
+                           realtype rtol, realtype atol, realtype out[2]) {
   if (s < 1 || s > CRD_ARK_MAX_LINCOMB || !hb || !hd || !yn || !F || !ynew || !out) { set_error("N_VErkFinish_Crd: bad arguments"); return -1; }
   crd_ctx *c = CTX(yn);
   const long long len = LEN(yn);
   if (use(c)) return -1;
-  out[0] = out[1] = 0.0;
+  double hi = 0.0, lo = 0.0, y2 = 0.0;
   if (len > 0) {
     FinishArgs a;
     for (int j = 0; j < s; ++j) {
@@ -505,28 +601,48 @@ int N_VErkFinish_Crd(int s, const realtype *hb, const realtype *hd, N_Vector yn,
     }
     a.yn = D(yn); a.ynew = D(ynew); a.rtol = rtol; a.atol = atol;
     if (((uintptr_t)a.yn | (uintptr_t)a.ynew) & 15) { set_error("N_VErkFinish_Crd: vectors must be 16-byte aligned"); return -1; }
-    unsigned int blocks = grid_for((len + 1) / 2);
+    unsigned int blocks = grid_for((len + 1) / 2, c->sms);
     if (blocks > (unsigned)kRedBlocks) blocks = kRedBlocks;
+#define CRD_FIN_CASE(S_)                                                                                                     \
+  case S_:                                                                                                                   \
+    if (seq) erk_finish_kernel<S_, true><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev); \
+    else erk_finish_kernel<S_, false><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev);    \
+    break;
     switch (s) {
-      case 1: erk_finish_kernel<1><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev); break;
-      case 2: erk_finish_kernel<2><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev); break;
-      case 3: erk_finish_kernel<3><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev); break;
-      case 4: erk_finish_kernel<4><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev); break;
-      case 5: erk_finish_kernel<5><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev); break;
-      case 6: erk_finish_kernel<6><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev); break;
-      case 7: erk_finish_kernel<7><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev); break;
-      default: erk_finish_kernel<8><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev); break;
+      CRD_FIN_CASE(1) CRD_FIN_CASE(2) CRD_FIN_CASE(3) CRD_FIN_CASE(4) CRD_FIN_CASE(5) CRD_FIN_CASE(6) CRD_FIN_CASE(7)
+      default:
+        if (seq) erk_finish_kernel<8, true><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev);
+        else erk_finish_kernel<8, false><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev);
+        break;
     }
+#undef CRD_FIN_CASE
     if (check_launch(c, "erk_finish_kernel")) return -1;
-    CRD_CUDA(cudaStreamSynchronize(c->stream));
-    out[0] = c->red_result_host[0];
-    out[1] = c->red_result_host[1];
+    if (sync_stream(c, "N_VErkFinish_Crd")) return -1;
+    hi = c->red_result_host[0]; y2 = c->red_result_host[1]; lo = c->red_result_host[2];
   }
-  if (c->nranks > 1 && c->allreduce(out, 2, CRD_SUM, c->allreduce_user) != 0) { set_error("N_VErkFinish_Crd: allreduce hook failed"); return -1; }
+  if (allreduce_dd(c, hi, lo, &y2)) return -1;
+  out[0] = hi + lo;
+  out[1] = y2;
   return 0;
+}
+
+int N_VErkFinish_Crd(int s, const realtype *hb, const realtype *hd, N_Vector yn, N_Vector *F, N_Vector ynew,
+                     realtype rtol, realtype atol, realtype out[2]) {
+  return erk_finish_impl(false, s, hb, hd, yn, F, ynew, rtol, atol, out);
+}
+int N_VErkFinishSeq_Crd(int s, const realtype *hb, const realtype *hd, N_Vector yn, N_Vector *F, N_Vector ynew,
+                        realtype rtol, realtype atol, realtype out[2]) {
+  return erk_finish_impl(true, s, hb, hd, yn, F, ynew, rtol, atol, out);
 }
 
 const crd_fused_ops *crd_nv_fused_ops(void) { return &g_fused; }
 const crd_fused_ops *crd_nv_fused_vector_ops(void) { return &g_fused_ops_only; }
+const crd_fused_ops *crd_nv_fused_ops_exact(void) { return &g_fused_exact; }
+const crd_fused_ops *crd_nv_fused_vector_ops_exact(void) { return &g_fused_exact_ops_only; }
+const crd_fused_ops *crd_nv_fused_ops_for(const crd_grid *g) {
+  crd_params p;
+  if (!g || crd_grid_params(g, &p) != 0) return nullptr;
+  return p.arith == CRD_ARITH_EXACT ? &g_fused_exact : &g_fused;
+}
 
 }  // extern "C"

@@ -77,7 +77,7 @@ struct ResArgs {
   double tn, next_h, hold, eta, etamax, eh0, eh1, ynorm_sq;
   // synchronisation, exchange, results
   unsigned long long *bar;   // [0] arrival counter (monotonic within a launch), [16] abort flag
-  double *partial;           // [2][gridDim.x]
+  double *partial;           // [3][gridDim.x]: error sum hi | sum (ynew w')^2 | error sum lo
   double *xch;               // [2 parities][gridDim.x bands][2 sides][nx]: u of the band's first / last row
   ResOut *out;
 };
@@ -158,7 +158,7 @@ struct PassCfg {
 };
 
 // phase 1: the stage state of every point of the band -> tile; its first / last row's u -> exchange buffer
-template <int N, int U>   // U: rows in flight per thread
+template <bool SEQ, int N, int U>   // U: rows in flight per thread
 __device__ __forceinline__ void phase1_n(const Comb &cb, const PassCfg &c, double2 *tile, double *xch_mine) {
   if (c.ty >= c.G) return;
   const int nx = c.nx, rows = c.rows, stride = c.G * nx;
@@ -175,10 +175,11 @@ __device__ __forceinline__ void phase1_n(const Comb &cb, const PassCfg &c, doubl
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int r = r0 + u * c.G;
-        // sum_j c_j x_j in the operation order of state2<true> / lincomb_kernel
-        double2 s = make_double2(cb.c[0] * v[u][0].x, cb.c[0] * v[u][0].y);
+        // sum_j c_j x_j in the operation order of state2<true, SEQ> (crd_fused.cuh)
+        double cc[N], vx[N], vy[N];
 #pragma unroll
-        for (int j = 1; j < N; ++j) { s.x = fma(cb.c[j], v[u][j].x, s.x); s.y = fma(cb.c[j], v[u][j].y, s.y); }
+        for (int j = 0; j < N; ++j) { cc[j] = cb.c[j]; vx[j] = v[u][j].x; vy[j] = v[u][j].y; }
+        const double2 s = make_double2(lc_value_n<SEQ, N>(cc, vx), lc_value_n<SEQ, N>(cc, vy));
         if (r < rows) {
           tile[p0 + u * stride] = s;
           if (r == 0) xch_mine[i] = s.x;
@@ -188,14 +189,14 @@ __device__ __forceinline__ void phase1_n(const Comb &cb, const PassCfg &c, doubl
     }
   }
 }
-template <int U>
+template <bool SEQ, int U>
 __device__ __forceinline__ void phase1(const Comb &cb, const PassCfg &c, double2 *tile, double *xch_mine) {
   switch (cb.n) {
-    case 1: phase1_n<1, U>(cb, c, tile, xch_mine); break;
-    case 2: phase1_n<2, U>(cb, c, tile, xch_mine); break;
-    case 3: phase1_n<3, U>(cb, c, tile, xch_mine); break;
-    case 4: phase1_n<4, (U > 2 ? 2 : U)>(cb, c, tile, xch_mine); break;    // wide combinations: fewer rows in flight (registers)
-    default: phase1_n<5, (U > 2 ? 2 : U)>(cb, c, tile, xch_mine); break;
+    case 1: phase1_n<SEQ, 1, U>(cb, c, tile, xch_mine); break;
+    case 2: phase1_n<SEQ, 2, U>(cb, c, tile, xch_mine); break;
+    case 3: phase1_n<SEQ, 3, U>(cb, c, tile, xch_mine); break;
+    case 4: phase1_n<SEQ, 4, (U > 2 ? 2 : U)>(cb, c, tile, xch_mine); break;    // wide combinations: fewer rows in flight (registers)
+    default: phase1_n<SEQ, 5, (U > 2 ? 2 : U)>(cb, c, tile, xch_mine); break;
   }
 }
 
@@ -205,7 +206,7 @@ __device__ __forceinline__ void phase1(const Comb &cb, const PassCfg &c, double2
 // (crd_fused.cuh arithmetic).
 template <int MODEL, bool EXACT, bool FIN>
 __device__ __forceinline__ void phase2_rows(const PassCfg &c, const RhsConst &k_in, const double2 *tile, const double *xs, const double *xn,
-                                            double2 *out, const ResFinish *fin, int r_first, int r_step, int nr, double &e2, double &y2) {
+                                            double2 *out, const ResFinish *fin, int r_first, int r_step, int nr, FinAcc<EXACT> &facc) {
   if (c.ty >= c.G) return;
   const int nx = c.nx, rows = c.rows;
   const int S = FIN ? fin->s : 0;
@@ -241,13 +242,13 @@ __device__ __forceinline__ void phase2_rows(const PassCfg &c, const RhsConst &k_
         for (int j = 0; j < kResStages; ++j) {
           if (j < S) {
             const double2 fj = (j == S - 1) ? make_double2(du, dv) : fin->F[j][p];
-            sx = fma(fin->hb[j], fj.x, sx); ex = fma(fin->hd[j], fj.x, ex);
-            sy = fma(fin->hb[j], fj.y, sy); ey = fma(fin->hd[j], fj.y, ey);
+            sx = fin_sol_term<EXACT>(fin->hb[j], fj.x, sx); ex = fin_err_term<EXACT>(fin->hd[j], fj.x, ex);
+            sy = fin_sol_term<EXACT>(fin->hb[j], fj.y, sy); ey = fin_err_term<EXACT>(fin->hd[j], fj.y, ey);
           }
         }
         fin->ynew[p] = make_double2(sx, sy);
-        finish_tail_rcp(fin->rtol, fin->atol, y0.x, sx, ex, e2, y2);
-        finish_tail_rcp(fin->rtol, fin->atol, y0.y, sy, ey, e2, y2);
+        finish_tail<EXACT>(fin->rtol, fin->atol, y0.x, sx, ex, facc);
+        finish_tail<EXACT>(fin->rtol, fin->atol, y0.y, sy, ey, facc);
       }
     }
   }
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(NT, 1) erk_resident_kernel(const ResArgs P) {
   __shared__ ResFinish sf;
   __shared__ ResLoop L;
   __shared__ double2 *S[ST_N];    // band-local base of each storage (generic address: shared or global)
-  __shared__ double s_red[2][NW];
+  __shared__ double s_red[3][NW];
   __shared__ int s_ok;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nb = gridDim.x, b = blockIdx.x;
@@ -381,14 +382,14 @@ __global__ void __launch_bounds__(NT, 1) erk_resident_kernel(const ResArgs P) {
   //   phase 1 of the pass's state, arrive | interior rows | wait | [after the last stage: error test] | edge rows
   bool alive = true;
   int is = 1;                       // the pass: stage `is` for is < s, is == s: fnew of the state the last stage produced
-  double e2 = 0.0, y2 = 0.0;
+  FinAcc<EXACT> facc;
   while (L.status != 2) {
     const int s_ = P.s;
     const bool fnew_pass = (is == s_), last = (is == s_ - 1);
     const double h = L.h;
     tick(4);
     // phase 1: this pass's state into the tile, the band's edge rows into the exchange buffer; then arrive
-    phase1<4>(fnew_pass ? identity_comb(ST_Y0 + (L.yi ^ 1)) : stage_comb(is, h), cfg, tile, xch_mine(L.pass));
+    phase1<EXACT, 4>(fnew_pass ? identity_comb(ST_Y0 + (L.yi ^ 1)) : stage_comb(is, h), cfg, tile, xch_mine(L.pass));
     if (last && threadIdx.x == 0) {
       sf.yn = S[ST_Y0 + L.yi]; sf.ynew = S[ST_Y0 + (L.yi ^ 1)];
       for (int j = 0; j < s_; ++j) {
@@ -415,11 +416,11 @@ __global__ void __launch_bounds__(NT, 1) erk_resident_kernel(const ResArgs P) {
         if (fnew_pass) {
           // ---- error norm: every CTA adds all partials in the same order, then the same test and controller ----
           if (warp == 0) {
-            double se = 0.0, sy = 0.0;
-            for (int q = lane; q < nb; q += 32) { se += __ldcg(P.partial + q); sy += __ldcg(P.partial + nb + q); }
+            double se = 0.0, sl = 0.0, sy = 0.0;   // the error sum as a double-double pair, merged in a fixed order, rounded once
+            for (int q = lane; q < nb; q += 32) { dd_merge(se, sl, __ldcg(P.partial + q), __ldcg(P.partial + 2 * nb + q)); sy += __ldcg(P.partial + nb + q); }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { se += __shfl_down_sync(0xffffffffu, se, o); sy += __shfl_down_sync(0xffffffffu, sy, o); }
-            se = __shfl_sync(0xffffffffu, se, 0);
+            for (int o = 16; o > 0; o >>= 1) { dd_shfl_down(se, sl, o); sy += __shfl_down_sync(0xffffffffu, sy, o); }
+            se = __shfl_sync(0xffffffffu, __dadd_rn(se, sl), 0);
             const double dsm = sqrt(se / P.nglobal);
             const double eta_a = res_adapt_eta(P, L.h, dsm, L.eh0, L.eh1, L.etamax, lane);
             const double eta_r = res_adapt_eta(P, L.h, dsm, L.eh0, L.eh1, 1.0, lane);   // after a failure etamax is 1
@@ -460,8 +461,8 @@ __global__ void __launch_bounds__(NT, 1) erk_resident_kernel(const ResArgs P) {
           r_first = 0; r_step = cfg.rows - 1; nr = n_edge;
         }
       }
-      if (last) phase2_rows<MODEL, EXACT, true>(cfg, sk, tile, xs, xn, out, &sf, r_first, r_step, nr, e2, y2);
-      else phase2_rows<MODEL, EXACT, false>(cfg, sk, tile, xs, xn, out, nullptr, r_first, r_step, nr, e2, y2);
+      if (last) phase2_rows<MODEL, EXACT, true>(cfg, sk, tile, xs, xn, out, &sf, r_first, r_step, nr, facc);
+      else phase2_rows<MODEL, EXACT, false>(cfg, sk, tile, xs, xn, out, nullptr, r_first, r_step, nr, facc);
       tick(part == 0 ? 1 : 3);
     }
     if (!alive) break;
@@ -472,18 +473,20 @@ __global__ void __launch_bounds__(NT, 1) erk_resident_kernel(const ResArgs P) {
     }
     if (last) {
       // CTA partial sums, fixed order: shuffle tree, then the warps in order
+      double eh = facc.e_hi, el = facc.e_lo, y2 = facc.y2;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { e2 += __shfl_down_sync(0xffffffffu, e2, o); y2 += __shfl_down_sync(0xffffffffu, y2, o); }
-      if (lane == 0) { s_red[0][warp] = e2; s_red[1][warp] = y2; }
-      e2 = 0.0; y2 = 0.0;
+      for (int o = 16; o > 0; o >>= 1) { dd_shfl_down(eh, el, o); y2 += __shfl_down_sync(0xffffffffu, y2, o); }
+      if (lane == 0) { s_red[0][warp] = eh; s_red[1][warp] = y2; s_red[2][warp] = el; }
+      facc = FinAcc<EXACT>();
     }
     __syncthreads();          // every read of the tile is done; the band's F_is / ynew / fnew is complete
     if (threadIdx.x == 0) {
       if (last) {
-        double se = s_red[0][0], sy = s_red[1][0];
-        for (int w = 1; w < NW; ++w) { se += s_red[0][w]; sy += s_red[1][w]; }
+        double se = s_red[0][0], sy = s_red[1][0], sl = s_red[2][0];
+        for (int w = 1; w < NW; ++w) { dd_merge(se, sl, s_red[0][w], s_red[2][w]); sy += s_red[1][w]; }
         P.partial[b] = se;
         P.partial[nb + b] = sy;
+        P.partial[2 * nb + b] = sl;
       }
       if (is == 1) L.attempts++;
       L.nfe++;
@@ -543,7 +546,11 @@ ResKernel *res_kernel_entry() {
 // ticks: the instantiation with per-phase cycle counters (crd_grid_resident_cycles), selected by grid variant 150
 template <int MODEL, bool EXACT>
 ResKernel *res_pick_nt(int ticks) {
-  return ticks ? res_kernel_entry<MODEL, EXACT, 512, true>() : res_kernel_entry<MODEL, EXACT, 512, false>();
+#ifdef CRD_PROFILING_VARIANTS
+  if (ticks) return res_kernel_entry<MODEL, EXACT, 512, true>();
+#endif
+  (void)ticks;
+  return res_kernel_entry<MODEL, EXACT, 512, false>();
 }
 
 ResKernel *res_pick(int model, bool exact, int ticks) {
@@ -661,11 +668,11 @@ int crd_erk_evolve(struct crd_erk_state *st, void *user_data) {
   // scratch: barrier words, partials, exchange rows, result block (kept with the grid)
   if (!g->res_bar) {
     CRD_CUDA(cudaMalloc(&g->res_bar, 32 * sizeof(unsigned long long)));
-    CRD_CUDA(cudaMalloc(&g->res_partial, sizeof(double) * (2 * (size_t)sms + 4 * (size_t)sms * (size_t)g->nx)));
+    CRD_CUDA(cudaMalloc(&g->res_partial, sizeof(double) * (4 * (size_t)sms + 4 * (size_t)sms * (size_t)g->nx)));
     CRD_CUDA(cudaHostAlloc(&g->res_out_host, sizeof(ResOut), cudaHostAllocMapped));
     CRD_CUDA(cudaHostGetDevicePointer(&g->res_out_dev, g->res_out_host, 0));
   }
-  P.bar = g->res_bar; P.partial = g->res_partial; P.xch = g->res_partial + 2 * (size_t)sms; P.out = (ResOut *)g->res_out_dev;
+  P.bar = g->res_bar; P.partial = g->res_partial; P.xch = g->res_partial + 4 * (size_t)sms; P.out = (ResOut *)g->res_out_dev;
   ResOut *out = (ResOut *)g->res_out_host;
   std::memset(out, 0, sizeof *out);
   CRD_CUDA(cudaMemsetAsync(g->res_bar, 0, 32 * sizeof(unsigned long long), ctx->stream));
@@ -681,7 +688,7 @@ int crd_erk_evolve(struct crd_erk_state *st, void *user_data) {
   }
   ctx->launches++;
   g->resident_launches++;
-  CRD_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (sync_stream(ctx, "crd_erk_evolve")) return -1;
   if (!out->done || out->err) { set_error("crd_erk_evolve: the device step loop did not complete (grid barrier timed out)"); return -1; }
 
   st->tn = out->tn; st->next_h = out->next_h; st->hold = out->hold; st->eta = out->eta; st->etamax = out->etamax;

@@ -144,8 +144,9 @@ static int launch_push(crd_grid *g, const StateRef &S, cudaStream_t st) {
   RhsArgs a = make_args(g, 0.0, S, nullptr, 0, g->nyl, slab_row(0), slab_row(0));
   double *pn = (double *)(g->halo_prev + L.ghost_off(par, 1)), *ns = (double *)(g->halo_next + L.ghost_off(par, 0));
   unsigned long long *pf = (unsigned long long *)(g->halo_prev + L.flag_off(1)), *nf = (unsigned long long *)(g->halo_next + L.flag_off(0));
-  if (S.n > 0) halo_push_kernel<true><<<kPushBlocks, 256, 0, st>>>(a, pn, ns, pf, nf, g->push_ticket, g->epoch);
-  else halo_push_kernel<false><<<kPushBlocks, 256, 0, st>>>(a, pn, ns, pf, nf, g->push_ticket, g->epoch);
+  if (S.n > 0 && g->p.arith == CRD_ARITH_EXACT) halo_push_kernel<true, true><<<kPushBlocks, 256, 0, st>>>(a, pn, ns, pf, nf, g->push_ticket, g->epoch);
+  else if (S.n > 0) halo_push_kernel<true, false><<<kPushBlocks, 256, 0, st>>>(a, pn, ns, pf, nf, g->push_ticket, g->epoch);
+  else halo_push_kernel<false, false><<<kPushBlocks, 256, 0, st>>>(a, pn, ns, pf, nf, g->push_ticket, g->epoch);
   return check_launch(g->ctx, "halo_push_kernel");
 }
 
@@ -192,7 +193,7 @@ struct FinCtx {
   int nregions = 0;
   int nblocks[3] = {0, 0, 0};
 };
-constexpr int kFinRegion = 2 * kRedBlocks;   // doubles per region: [2][kRedBlocks]
+constexpr int kFinRegion = 3 * kRedBlocks;   // doubles per region: [3][kRedBlocks]
 
 static int launch_part(crd_grid *g, const RhsArgs &a, cudaStream_t st, FinCtx *fc) {
   if (!fc) return launch_rhs(g, a, st);
@@ -311,10 +312,11 @@ int crd_rhs_lincomb_finish(crd_grid *g, double t, int s, const double *c, const 
   // every launch has been joined into the main stream: add the regions in a fixed order
   fin_reduce_kernel<<<1, 256, 0, ctx->stream>>>(g->fin_partial, fc.nregions, fc.nblocks[0], fc.nblocks[1], fc.nblocks[2], ctx->red_result_dev);
   if (check_launch(ctx, "fin_reduce_kernel")) return -1;
-  CRD_CUDA(cudaStreamSynchronize(ctx->stream));
-  out[0] = ctx->red_result_host[0];
-  out[1] = ctx->red_result_host[1];
-  if (ctx->nranks > 1 && ctx->allreduce(out, 2, CRD_SUM, ctx->allreduce_user) != 0) { set_error("crd_rhs_lincomb_finish: allreduce hook failed"); return -1; }
+  if (sync_stream(ctx, "crd_rhs_lincomb_finish")) return -1;
+  double hi = ctx->red_result_host[0], y2 = ctx->red_result_host[1], lo = ctx->red_result_host[2];
+  if (allreduce_dd(ctx, hi, lo, &y2)) return -1;   // the ranks' pairs merged in rank order: same bits on every rank and for any split
+  out[0] = hi + lo;
+  out[1] = y2;
   return 0;
 }
 

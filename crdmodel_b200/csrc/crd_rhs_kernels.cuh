@@ -36,17 +36,17 @@ __global__ void __launch_bounds__(256, MINB) rhs_kernel(const RhsArgs a) {
   for (int r = 0; r < RY; ++r) {
     if (r < nrows) {
       const long long row = (j0 + r) * nx;
-      c[r] = state2<LC>(a, row + i);
-      uw[r] = stateu<LC>(a, row + iw);
-      ue[r] = stateu<LC>(a, row + ie);
+      c[r] = state2<LC, EXACT>(a, row + i);
+      uw[r] = stateu<LC, EXACT>(a, row + iw);
+      ue[r] = stateu<LC, EXACT>(a, row + ie);
     } else {
       c[r] = make_double2(0.0, 0.0); uw[r] = 0.0; ue[r] = 0.0;
     }
   }
-  uu[0] = (j0 == 0) ? ghost_u<LC>(a, a.south, a.south_off, i) : stateu<LC>(a, (j0 - 1) * nx + i);
+  uu[0] = (j0 == 0) ? ghost_u<LC, EXACT>(a, a.south, a.south_off, i) : stateu<LC, EXACT>(a, (j0 - 1) * nx + i);
   {
     const long long jn = j0 + nrows;  // row above the last one this thread computes
-    uu[RY + 1] = (jn == nyl) ? ghost_u<LC>(a, a.north, a.north_off, i) : stateu<LC>(a, jn * nx + i);
+    uu[RY + 1] = (jn == nyl) ? ghost_u<LC, EXACT>(a, a.north, a.north_off, i) : stateu<LC, EXACT>(a, jn * nx + i);
   }
 #pragma unroll
   for (int r = 0; r < RY; ++r) uu[r + 1] = c[r].x;
@@ -113,7 +113,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
-template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, bool LC, int NG, bool LCT = false>
+template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, bool LC, int NG>
 __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   constexpr int PITCH = TX + 2;            // points per staged row (west halo + TX + east halo)
   constexpr int RPT = TY * TX / 256;       // rows marched by one thread
@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   constexpr int GR = (TY + 2 + NG - 1) / NG;
   static_assert(256 % TX == 0 && (TY * TX) % 256 == 0, "tile shape");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double2 *tile = reinterpret_cast<double2 *>(smem_raw);                      // [TY+2][PITCH]  (LCT: one such tile per input vector)
+  double2 *tile = reinterpret_cast<double2 *>(smem_raw);                      // [TY+2][PITCH]
   constexpr size_t kTileBytes = (size_t)(TY + 2) * PITCH * 16;
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + kTileBytes * (LCT ? (size_t)a.nlc : 1));
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + kTileBytes);
 
   const long long nx = a.nx, nyl = a.nyl;
   const long long tiles_x = (nx + TX - 1) / TX;
@@ -160,39 +160,6 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
     }
   }
   __syncthreads();   // barrier initialised before anyone polls it
-  } else if (LCT) {
-    // fused stage assembly, TMA-staged: the raw tile of EVERY input vector arrives by 1-D bulk copies in the same NG row
-    // groups as a plain state (no thread computes a load address, no registers hold data in flight, no staging pass); the
-    // march below forms sum_j c_j x_j of each value it reads, in the operation order of state2<true> / lincomb_kernel.
-    const int nv = a.nlc;
-    const bool ext_s = (j0 == 0) && a.south != nullptr, ext_n = (j0 + h == nyl) && a.north != nullptr;   // already combined ghost rows
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int gi = 0; gi < NG; ++gi) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8u * gi) : "memory");
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      const bool west_in = i0 > 0, east_in = i0 + w < nx;
-      const unsigned row_bytes = (unsigned)(w + (west_in ? 1 : 0) + (east_in ? 1 : 0)) * 16u;
-      for (int gi = 0; gi < NG; ++gi) {
-        const int ra = gi * GR, rb = (ra + GR < h + 2) ? ra + GR : h + 2;
-        unsigned gbytes = 0;
-        for (int r = ra; r < rb; ++r) gbytes += (unsigned)(((r == 0 && ext_s) || (r == h + 1 && ext_n)) ? 1 : nv) * (unsigned)(w + 2) * 16u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar + 8u * gi), "r"(gbytes) : "memory");
-        for (int r = ra; r < rb; ++r) {
-          const long long jr = j0 - 1 + r;
-          const bool ext = (r == 0 && ext_s) || (r == h + 1 && ext_n);
-          for (int j = 0; j < (ext ? 1 : nv); ++j) {
-            const double2 *row;
-            if (ext) row = reinterpret_cast<const double2 *>(jr < 0 ? a.south : a.north);
-            else row = reinterpret_cast<const double2 *>(a.lc_x[j]) + ((jr < 0) ? a.south_off : (jr >= nyl) ? a.north_off : jr * nx);
-            const unsigned dst = smem_u32(smem_raw + kTileBytes * j) + (unsigned)(r * PITCH) * 16u;
-            bulk_g2s(dst + (west_in ? 0u : 16u), row + i0 - (west_in ? 1 : 0), row_bytes, bar + 8u * gi);
-            if (!west_in) bulk_g2s(dst, row + (nx - 1), 16u, bar + 8u * gi);
-            if (!east_in) bulk_g2s(dst + (unsigned)(w + 1) * 16u, row, 16u, bar + 8u * gi);
-          }
-        }
-      }
-    }
-    __syncthreads();   // barriers initialised before anyone polls them
   } else {
     // fused stage assembly: the tile is the combination sum_j c_j x_j, formed while it is staged (the stage
     // state is never written to HBM).  Plain coalesced 16-byte loads; each thread stages its own column, nine
@@ -201,9 +168,9 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
       const long long jr = j0 - 1 + r;
       const long long col = (sc == 0) ? (i0 == 0 ? nx - 1 : i0 - 1) : (sc == w + 1) ? (i0 + w == nx ? 0 : i0 + w) : i0 + sc - 1;
       double2 v;
-      if (jr < 0) v = a.south ? reinterpret_cast<const double2 *>(a.south)[col] : state2<true>(a, a.south_off + col);
-      else if (jr >= nyl) v = a.north ? reinterpret_cast<const double2 *>(a.north)[col] : state2<true>(a, a.north_off + col);
-      else v = state2<true>(a, jr * nx + col);
+      if (jr < 0) v = a.south ? reinterpret_cast<const double2 *>(a.south)[col] : state2<true, EXACT>(a, a.south_off + col);
+      else if (jr >= nyl) v = a.north ? reinterpret_cast<const double2 *>(a.north)[col] : state2<true, EXACT>(a, a.north_off + col);
+      else v = state2<true, EXACT>(a, jr * nx + col);
       tile[r * PITCH + sc] = v;
     };
     const int r_lo = (j0 == 0) ? 1 : 0, r_hi = (j0 + h == nyl) ? h + 1 : h + 2;   // tile rows that are rows of this launch
@@ -212,19 +179,44 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
       const long long p0 = (j0 - 1) * nx + i0 + tcol;   // point offset of tile row 0 in this column
       for (int rb = r_lo; rb < r_hi; rb += R) {
         double2 acc[R], v[R];
+        auto load = [&](int j) {
 #pragma unroll
-        for (int rr = 0; rr < R; ++rr)
-          v[rr] = (rb + rr < r_hi) ? reinterpret_cast<const double2 *>(a.lc_x[0])[p0 + (rb + rr) * nx] : make_double2(0.0, 0.0);
+          for (int rr = 0; rr < R; ++rr)
+            v[rr] = (rb + rr < r_hi) ? reinterpret_cast<const double2 *>(a.lc_x[j])[p0 + (rb + rr) * nx] : make_double2(0.0, 0.0);
+        };
+        if constexpr (!EXACT) {
+          load(0);
 #pragma unroll
-        for (int rr = 0; rr < R; ++rr) acc[rr] = make_double2(a.lc_c[0] * v[rr].x, a.lc_c[0] * v[rr].y);
+          for (int rr = 0; rr < R; ++rr) acc[rr] = make_double2(a.lc_c[0] * v[rr].x, a.lc_c[0] * v[rr].y);
 #pragma unroll
-        for (int j = 1; j < kMaxLc; ++j) {
-          if (j < a.nlc) {
+          for (int j = 1; j < kMaxLc; ++j) {
+            if (j < a.nlc) {
+              load(j);
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr)
-              v[rr] = (rb + rr < r_hi) ? reinterpret_cast<const double2 *>(a.lc_x[j])[p0 + (rb + rr) * nx] : make_double2(0.0, 0.0);
+              for (int rr = 0; rr < R; ++rr) { acc[rr].x = fma(a.lc_c[j], v[rr].x, acc[rr].x); acc[rr].y = fma(a.lc_c[j], v[rr].y, acc[rr].y); }
+            }
+          }
+        } else {
+          // the order of lc_value<true>: the increments first (sdata), the vector they are added to last
+          if (a.nlc > 1) {
+            load(1);
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr) { acc[rr].x = fma(a.lc_c[j], v[rr].x, acc[rr].x); acc[rr].y = fma(a.lc_c[j], v[rr].y, acc[rr].y); }
+            for (int rr = 0; rr < R; ++rr) acc[rr] = make_double2(__dadd_rn(__dmul_rn(a.lc_c[1], v[rr].x), 0.0), __dadd_rn(__dmul_rn(a.lc_c[1], v[rr].y), 0.0));
+#pragma unroll
+            for (int j = 2; j < kMaxLc; ++j) {
+              if (j < a.nlc) {
+                load(j);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) { acc[rr].x = __dadd_rn(__dmul_rn(a.lc_c[j], v[rr].x), acc[rr].x); acc[rr].y = __dadd_rn(__dmul_rn(a.lc_c[j], v[rr].y), acc[rr].y); }
+              }
+            }
+            load(0);
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) { acc[rr].x = __dadd_rn(__dmul_rn(a.lc_c[0], v[rr].x), acc[rr].x); acc[rr].y = __dadd_rn(__dmul_rn(a.lc_c[0], v[rr].y), acc[rr].y); }
+          } else {
+            load(0);
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) acc[rr] = make_double2(__dmul_rn(a.lc_c[0], v[rr].x), __dmul_rn(a.lc_c[0], v[rr].y));
           }
         }
 #pragma unroll
@@ -254,39 +246,14 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
     }
   };
   // rows g0, g0+1, g0+2 of the tile are needed before the first output row
-  if (!LC || LCT) {
+  if (!LC) {
     for (int gi = 0; gi <= (g0 + 2) / GR; ++gi) wait_group(gi);
   }
   if (!active) return;
 
   const double2 *col = tile + (g0 + 1) * PITCH + (c + 1);   // centre of this thread's first row
-  // LCT: the value at tile offset `off` (relative to col) is the combination of the raw tiles; row `tr` of the tile may be
-  // a ghost row that arrived already combined (ring: first tile only)
-  const bool lct_ext_s = LCT && (j0 == 0) && a.south != nullptr, lct_ext_n = LCT && (j0 + h == nyl) && a.north != nullptr;
-  auto rd2 = [&](int off, int tr) -> double2 {
-    const double2 v0 = col[off];
-    if (!LCT) return v0;
-    if ((tr == 0 && lct_ext_s) || (tr == h + 1 && lct_ext_n)) return v0;
-    double2 sacc = make_double2(a.lc_c[0] * v0.x, a.lc_c[0] * v0.y);
-#pragma unroll
-    for (int j = 1; j < kMaxLc; ++j)
-      if (j < a.nlc) {
-        const double2 v = reinterpret_cast<const double2 *>(reinterpret_cast<const unsigned char *>(col) + kTileBytes * j)[off];
-        sacc.x = fma(a.lc_c[j], v.x, sacc.x); sacc.y = fma(a.lc_c[j], v.y, sacc.y);
-      }
-    return sacc;
-  };
-  auto rdx = [&](int off) -> double {   // u only, never a ghost row (west / east neighbours of the thread's own rows)
-    const double v0 = col[off].x;
-    if (!LCT) return v0;
-    double sacc = a.lc_c[0] * v0;
-#pragma unroll
-    for (int j = 1; j < kMaxLc; ++j)
-      if (j < a.nlc) sacc = fma(a.lc_c[j], reinterpret_cast<const double2 *>(reinterpret_cast<const unsigned char *>(col) + kTileBytes * j)[off].x, sacc);
-    return sacc;
-  };
-  double uS = rd2(-PITCH, g0).x;
-  double2 cc = rd2(0, g0 + 1);
+  double uS = col[-PITCH].x;
+  double2 cc = col[0];
   double2 *out = reinterpret_cast<double2 *>(a.ydot) + (j0 + g0) * nx + (i0 + c);
   const int nrows = (h - g0 < RPT) ? (h - g0) : RPT;
   const double *__restrict__ brow = a.brow + (j0 + g0);
@@ -294,9 +261,9 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   double2 *const out0 = out;
   bool bad = (ACC && EXACT && is_torus(MODEL)) ? (a.k.div_safe == 0) : false;
   auto row = [&](int r) {
-    if ((!LC || LCT) && r > 0 && (g0 + r + 2) % GR == 0 && (g0 + r + 2) / GR < NG) wait_group((g0 + r + 2) / GR);   // north row enters a new group
-    const double2 nn = rd2((r + 1) * PITCH, g0 + r + 2);
-    const double uW = rdx(r * PITCH - 1), uE = rdx(r * PITCH + 1);
+    if (!LC && r > 0 && (g0 + r + 2) % GR == 0 && (g0 + r + 2) / GR < NG) wait_group((g0 + r + 2) / GR);   // north row enters a new group
+    const double2 nn = col[(r + 1) * PITCH];
+    const double uW = col[r * PITCH - 1].x, uE = col[r * PITCH + 1].x;
     double du = !EXACT ? stencil_fast<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x)
                 : ACC  ? stencil_exact_acc<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x, bad)
                        : stencil_exact<MODEL>(a.k, t1, t3, cc.x, uW, uE, uS, nn.x);
@@ -342,27 +309,6 @@ int launch_tile_lc(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   kern<<<(unsigned)tiles, 256, smem, st>>>(a);
   return check_launch(g->ctx, "rhs_tile_kernel");
 }
-// fused stage assembly with TMA-staged raw tiles (2 or 3 input vectors; 128 x 16 tiles: 37 KB per vector, 3 CTAs per SM for 2),
-// the combination formed during the march (variant 30)
-template <int MODEL, bool EXACT>
-int launch_tile_lct(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
-  constexpr int TX = 128, TY = 16, NG = 3;
-  const long long tiles = ((a.nx + TX - 1) / TX) * ((a.nyl + TY - 1) / TY);
-  if (tiles <= 0) return 0;
-  if (tiles > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
-  const size_t smem = (size_t)(TY + 2) * (TX + 2) * 16 * (size_t)a.nlc + 8 * NG + 8;
-  auto kern = rhs_tile_kernel<MODEL, EXACT, TX, TY, 3, false, true, NG, true>;
-  static int attr_set[64] = {};   // per device: the largest size set so far
-  const int dev = g->ctx->device & 63;
-  if (attr_set[dev] < (int)smem) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
-    attr_set[dev] = (int)smem;
-  }
-  kern<<<(unsigned)tiles, 256, smem, st>>>(a);
-  return check_launch(g->ctx, "rhs_tile_kernel");
-}
-
 template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, int NG = 3>
 int launch_tile(crd_grid *g, const RhsArgs &a, cudaStream_t st) {
   return a.nlc > 0 ? launch_tile_lc<MODEL, EXACT, TX, TY, MINB, ACC, true, 1>(g, a, st)
@@ -399,7 +345,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 struct StageFin {
   double hb[kMaxLc], hd[kMaxLc];
   double rtol, atol;
-  double *partial;   // [2][kRedBlocks] per-CTA sums
+  double *partial;   // [3][kRedBlocks] per-CTA sums: error sum hi | sum (ynew w')^2 | error sum lo
 };
 
 // FIN = 2: the same arithmetic with a smaller register footprint (fits 3 CTAs per SM): instead of the raw vectors of the row
@@ -478,7 +424,7 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
   const int nxi = (int)nx, nyli = (int)nyl;
   int slot_i = 0;
   unsigned slot_par = 0;
-  double fe2 = 0.0, fy2 = 0.0;   // FIN: this thread's share of sum (err w)^2, sum (ynew w')^2
+  FinAcc<EXACT> facc;   // FIN: this thread's share of sum (err w)^2 (double-double when EXACT), sum (ynew w')^2
   double lcc[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) lcc[j] = a.lc_c[j];
@@ -509,15 +455,17 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
       } else {
 #pragma unroll
         for (int j = 0; j < NV; ++j) v[j] = slot[j * PITCH + c + 1];
-        nn = make_double2(lcc[0] * v[0].x, lcc[0] * v[0].y);
+        double vx[NV], vy[NV];
 #pragma unroll
-        for (int j = 1; j < NV; ++j) { nn.x = fma(lcc[j], v[j].x, nn.x); nn.y = fma(lcc[j], v[j].y, nn.y); }
+        for (int j = 0; j < NV; ++j) { vx[j] = v[j].x; vy[j] = v[j].y; }
+        nn = make_double2(lc_value_n<EXACT, NV>(lcc, vx), lc_value_n<EXACT, NV>(lcc, vy));
         nW = __shfl_up_sync(0xffffffffu, nn.x, 1);
         nE = __shfl_down_sync(0xffffffffu, nn.x, 1);
         if (edge_lane) {   // the neighbour lives in another warp: combine its u from the slot
-          double e = lcc[0] * slot[edge_q].x;
+          double ve[NV];
 #pragma unroll
-          for (int j = 1; j < NV; ++j) e = fma(lcc[j], slot[j * PITCH + edge_q].x, e);
+          for (int j = 0; j < NV; ++j) ve[j] = slot[j * PITCH + edge_q].x;
+          const double e = lc_value_n<EXACT, NV>(lcc, ve);
           if (lane == 0) nW = e; else nE = e;
         }
       }
@@ -535,12 +483,12 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
       if constexpr (!FIN) {
         if (active) *out = make_double2(du, dv);
       } else if constexpr (FIN == 2) {
-        const double sx = fma(fz.hb[NV - 1], du, psum.x), ex = fma(fz.hd[NV - 1], du, perr.x);
-        const double sy = fma(fz.hb[NV - 1], dv, psum.y), ey = fma(fz.hd[NV - 1], dv, perr.y);
+        const double sx = fin_sol_term<EXACT>(fz.hb[NV - 1], du, psum.x), ex = fin_err_term<EXACT>(fz.hd[NV - 1], du, perr.x);
+        const double sy = fin_sol_term<EXACT>(fz.hb[NV - 1], dv, psum.y), ey = fin_err_term<EXACT>(fz.hd[NV - 1], dv, perr.y);
         if (active) {
           *out = make_double2(sx, sy);
-          finish_tail_rcp(fz.rtol, fz.atol, pv[0].x, sx, ex, fe2, fy2);
-          finish_tail_rcp(fz.rtol, fz.atol, pv[0].y, sy, ey, fe2, fy2);
+          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].x, sx, ex, facc);
+          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].y, sy, ey, facc);
         }
       } else {
         // ynew = yn + sum_j hb_j F_j, err = sum_j hd_j F_j with F_{NV-1} = (du, dv): the operation order of finish_elem
@@ -548,13 +496,13 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
           const double2 f = (j == NV - 1) ? make_double2(du, dv) : pv[j + 1 < NV ? j + 1 : 0];
-          sx = fma(fz.hb[j], f.x, sx); ex = fma(fz.hd[j], f.x, ex);
-          sy = fma(fz.hb[j], f.y, sy); ey = fma(fz.hd[j], f.y, ey);
+          sx = fin_sol_term<EXACT>(fz.hb[j], f.x, sx); ex = fin_err_term<EXACT>(fz.hd[j], f.x, ex);
+          sy = fin_sol_term<EXACT>(fz.hb[j], f.y, sy); ey = fin_err_term<EXACT>(fz.hd[j], f.y, ey);
         }
         if (active) {
           *out = make_double2(sx, sy);
-          finish_tail_rcp(fz.rtol, fz.atol, pv[0].x, sx, ex, fe2, fy2);
-          finish_tail_rcp(fz.rtol, fz.atol, pv[0].y, sy, ey, fe2, fy2);
+          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].x, sx, ex, facc);
+          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].y, sy, ey, facc);
         }
       }
       out += nx;
@@ -573,8 +521,8 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
 #pragma unroll
           for (int j = 0; j < NV - 1; ++j) {
             const double2 f = lds_f64x2(sa + (unsigned)((j + 1) * PITCH * 16));
-            psum.x = fma(fz.hb[j], f.x, psum.x); perr.x = fma(fz.hd[j], f.x, perr.x);
-            psum.y = fma(fz.hb[j], f.y, psum.y); perr.y = fma(fz.hd[j], f.y, perr.y);
+            psum.x = fin_sol_term<EXACT>(fz.hb[j], f.x, psum.x); perr.x = fin_err_term<EXACT>(fz.hd[j], f.x, perr.x);
+            psum.y = fin_sol_term<EXACT>(fz.hb[j], f.y, psum.y); perr.y = fin_err_term<EXACT>(fz.hd[j], f.y, perr.y);
           }
         }
       }
@@ -611,39 +559,42 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
   }
   if (FIN) {
     // per-CTA sums in a fixed order: shuffle tree, then the eight consumer warps in order (the producer warp has left:
-    // named barrier over the 256 consumer threads)
-    __shared__ double fin_red[2][8];
+    // named barrier over the 256 consumer threads); the error sum travels as a double-double pair
+    __shared__ double fin_red[3][8];
+    double eh = facc.e_hi, el = facc.e_lo, fy2 = facc.y2;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { fe2 += __shfl_down_sync(0xffffffffu, fe2, o); fy2 += __shfl_down_sync(0xffffffffu, fy2, o); }
-    if (lane == 0) { fin_red[0][warp] = fe2; fin_red[1][warp] = fy2; }
+    for (int o = 16; o > 0; o >>= 1) { dd_shfl_down(eh, el, o); fy2 += __shfl_down_sync(0xffffffffu, fy2, o); }
+    if (lane == 0) { fin_red[0][warp] = eh; fin_red[1][warp] = fy2; fin_red[2][warp] = el; }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (threadIdx.x == 0) {
-      double se = fin_red[0][0], sy = fin_red[1][0];
-      for (int w = 1; w < 8; ++w) { se += fin_red[0][w]; sy += fin_red[1][w]; }
-      fz.partial[blockIdx.x] = se;
+      double sh = fin_red[0][0], sy = fin_red[1][0], sl = fin_red[2][0];
+      for (int w = 1; w < 8; ++w) { dd_merge(sh, sl, fin_red[0][w], fin_red[2][w]); sy += fin_red[1][w]; }
+      fz.partial[blockIdx.x] = sh;
       fz.partial[kRedBlocks + blockIdx.x] = sy;
+      fz.partial[2 * kRedBlocks + blockIdx.x] = sl;
     }
   }
 }
 
-// adds the per-CTA sums of a FIN stage (up to three launches, one region of [2][kRedBlocks] each) in a fixed order; the two
-// results go to mapped pinned host memory
+// adds the per-CTA sums of a FIN stage (up to three launches, one region of [3][kRedBlocks] each) in a fixed order, the error
+// sum in double-double; result[0] = hi, result[1] = sum (ynew w')^2, result[2] = lo go to mapped pinned host memory
 __global__ void __launch_bounds__(256) fin_reduce_kernel(const double *partial, int nregions, int n0, int n1, int n2, double *result) {
-  __shared__ double sm[2][8];
+  __shared__ double sm[3][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double se = 0.0, sy = 0.0;
+  double sh = 0.0, sl = 0.0, sy = 0.0;
   for (int r = 0; r < nregions; ++r) {
-    const double *p = partial + (size_t)r * 2 * kRedBlocks;
+    const double *p = partial + (size_t)r * 3 * kRedBlocks;
     const int n = r == 0 ? n0 : r == 1 ? n1 : n2;
-    for (int b = threadIdx.x; b < n; b += 256) { se += p[b]; sy += p[kRedBlocks + b]; }
+    for (int b = threadIdx.x; b < n; b += 256) { dd_merge(sh, sl, p[b], p[2 * kRedBlocks + b]); sy += p[kRedBlocks + b]; }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { se += __shfl_down_sync(0xffffffffu, se, o); sy += __shfl_down_sync(0xffffffffu, sy, o); }
-  if (lane == 0) { sm[0][warp] = se; sm[1][warp] = sy; }
+  for (int o = 16; o > 0; o >>= 1) { dd_shfl_down(sh, sl, o); sy += __shfl_down_sync(0xffffffffu, sy, o); }
+  if (lane == 0) { sm[0][warp] = sh; sm[1][warp] = sy; sm[2][warp] = sl; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) { sm[0][0] += sm[0][w]; sm[1][0] += sm[1][w]; }
-    result[0] = sm[0][0]; result[1] = sm[1][0];
+    sh = sm[0][0]; sy = sm[1][0]; sl = sm[2][0];
+    for (int w = 1; w < 8; ++w) { dd_merge(sh, sl, sm[0][w], sm[2][w]); sy += sm[1][w]; }
+    result[0] = sh; result[1] = sy; result[2] = sl;
     __threadfence_system();
   }
 }
@@ -668,7 +619,7 @@ int launch_stream_nv(crd_grid *g, const RhsArgs &a, cudaStream_t st, const Stage
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
     attr_set[dev] = true;
   }
-  const long long ctas = units < (long long)MINB * kSMs ? units : (long long)MINB * kSMs;
+  const long long ctas = units < (long long)MINB * g->ctx->sms ? units : (long long)MINB * g->ctx->sms;
   StageFin fz;
   if (fin) fz = *fin; else std::memset(&fz, 0, sizeof fz);
   if (nblocks) *nblocks = (int)ctas;
@@ -696,7 +647,11 @@ int launch_stage_finish(crd_grid *g, const RhsArgs &a, const StageFin &fin, cuda
   // 4.90 ms at 16384^2 (EXACT; FAST 4.16 vs 4.79), same bits.  Variant 23: FIN 2 with 2 CTAs per SM; 24: FIN 1 (the raw vectors
   // in registers) with 2 CTAs per SM, the former default.  profiles/README.md
 #define CRD_FIN_(M, F, B) (exact ? launch_stream_nv<M, true, 5, false, F, B>(g, a, st, &fin, nblocks) : launch_stream_nv<M, false, 5, false, F, B>(g, a, st, &fin, nblocks))
+#ifdef CRD_PROFILING_VARIANTS
 #define CRD_FIN(M) (g->variant == 24 ? CRD_FIN_(M, 1, 2) : g->variant == 23 ? CRD_FIN_(M, 2, 2) : CRD_FIN_(M, 2, 3))
+#else
+#define CRD_FIN(M) CRD_FIN_(M, 2, 3)
+#endif
   switch (g->p.model) {
     case CRD_FHN_TORUS: return CRD_FIN(CRD_FHN_TORUS);
     case CRD_GOLDBETER_TORUS: return CRD_FIN(CRD_GOLDBETER_TORUS);
@@ -714,8 +669,9 @@ int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
   // reasonably full.  Small slabs (the reference's default 400x1600 / 100x400 grids live in L2 and are bound by
   // launch latency and by how many CTAs a partial wave gets): the direct kernel with 2 rows per thread.
   // explicit: direct kernel (rows per thread, min CTAs/SM) 1 (2,4) | 2 (8,2) | 3 (1,4) | 4 (4,3) | 5 (4,4)
-  //           tiled kernel (TX, TY, min CTAs/SM) 10 (128,16,4) | 11 (128,32,3) | 12 (64,32,4) | 13 (256,16,3) | 14 (128,16,3)
-  //           15 = 13 with flag-and-redo instead of a branch per point
+  //           tiled kernel (TX, TY, min CTAs/SM) 10 (128,16,4) | 13 (256,16,3) | 15 = 13 with flag-and-redo instead of a
+  //           branch per point; streaming kernel 20 (2 CTAs/SM) | 21 (3 CTAs/SM).  Tilings that measured slower (11, 12, 14,
+  //           16-18; 23 / 24 for the fused finish) are compiled only with -DCRD_PROFILING_VARIANTS.
   int variant = g->variant;
   if (variant == 0) {
     const long long pts = a_in.nx * a_in.nyl;
@@ -727,10 +683,6 @@ int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
   if (g->variant == 0 && a_in.nlc == 5 && a_in.nx >= 192 && a_in.nx * a_in.nyl >= (4LL << 20)) variant = 20;
   // 2 or 3 input vectors: the streaming kernel with 3 CTAs per SM (24 consumer warps) is 1-3 % / 13-15 % ahead of the staged tile
   if (g->variant == 0 && (a_in.nlc == 2 || a_in.nlc == 3) && a_in.nx >= 192 && a_in.nx * a_in.nyl >= (4LL << 20)) variant = 21;
-  if (variant == 30) {   // fused stage assembly with TMA-staged raw tiles (2 or 3 input vectors)
-    if (a_in.nlc == 2 || a_in.nlc == 3) return launch_tile_lct<MODEL, EXACT>(g, a_in, st);
-    variant = 13;
-  }
   if (variant == 21) {   // streaming kernel with 3 CTAs per SM (plain state, 2 or 3 input vectors)
     if (a_in.nlc == 2) return launch_stream_nv<MODEL, EXACT, 2, false, false, 3>(g, a_in, st);
     if (a_in.nlc == 3) return launch_stream_nv<MODEL, EXACT, 3, false, false, 3>(g, a_in, st);
@@ -744,14 +696,16 @@ int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
   }
   switch (variant) {
     case 10: return launch_tile<MODEL, EXACT, 128, 16, 4, false>(g, a_in, st);
+    case 13: return launch_tile<MODEL, EXACT, 256, 16, 3, false>(g, a_in, st);
+    case 15: return launch_tile<MODEL, EXACT, 256, 16, 3, true>(g, a_in, st);   // flag-and-redo instead of a branch per point
+#ifdef CRD_PROFILING_VARIANTS   // tilings that measured slower (profiles/README.md); not part of the shipped library
     case 11: return launch_tile<MODEL, EXACT, 128, 32, 3, false>(g, a_in, st);
     case 12: return launch_tile<MODEL, EXACT, 64, 32, 4, false>(g, a_in, st);
-    case 13: return launch_tile<MODEL, EXACT, 256, 16, 3, false>(g, a_in, st);
     case 14: return launch_tile<MODEL, EXACT, 128, 16, 3, false>(g, a_in, st);
-    case 15: return launch_tile<MODEL, EXACT, 256, 16, 3, true>(g, a_in, st);   // flag-and-redo instead of a branch per point
     case 16: return launch_tile<MODEL, EXACT, 256, 16, 3, false, 6>(g, a_in, st);  // tile arrives in 6 row groups
     case 17: return launch_tile<MODEL, EXACT, 256, 16, 3, false, 2>(g, a_in, st);  // ... in 2
     case 18: return launch_tile<MODEL, EXACT, 256, 16, 3, false, 9>(g, a_in, st);  // ... in 9
+#endif
     default: break;
   }
   const int RY = (variant == 1) ? 2 : (variant == 2) ? 8 : (variant == 3) ? 1 : 4;
@@ -839,7 +793,7 @@ RhsArgs make_args(const crd_grid *g, double t, const StateRef &S, double *ydot, 
 }
 
 // ---- halo ring: push first/last row into the neighbours' ghost blocks, flag the epoch ------------------
-template <bool LC>
+template <bool LC, bool SEQ>
 __global__ void __launch_bounds__(256) halo_push_kernel(const RhsArgs a, double *prev_north, double *next_south,
                                                         unsigned long long *prev_flag, unsigned long long *next_flag,
                                                         unsigned long long *ticket, unsigned long long epoch) {
@@ -847,8 +801,8 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const RhsArgs a, double 
   const long long stride = (long long)gridDim.x * blockDim.x;
   double2 *pn = reinterpret_cast<double2 *>(prev_north), *ns = reinterpret_cast<double2 *>(next_south);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nx; i += stride) {
-    pn[i] = state2<LC>(a, i);                     // my row js is the row above prev's je
-    ns[i] = state2<LC>(a, (nyl - 1) * nx + i);    // my row je is the row below next's js
+    pn[i] = state2<LC, SEQ>(a, i);                     // my row js is the row above prev's je
+    ns[i] = state2<LC, SEQ>(a, (nyl - 1) * nx + i);    // my row je is the row below next's js
   }
   __threadfence_system();
   __syncthreads();

@@ -3,6 +3,7 @@
 // the launch-per-evaluation kernels (crd_rhs_kernels.cuh) and the device-resident stepper (crd_resident.cu), so both
 // produce the same bits for the same state.
 #pragma once
+#include "crd_fused.cuh"
 #include "crd_grid.cuh"
 
 using namespace crd;
@@ -166,8 +167,10 @@ __device__ __forceinline__ void react(const RhsConst &k, double b, double u, dou
   }
 }
 
-// ---- state access: plain vector, or sum_j c_j x_j formed on the fly (same operation order as lincomb_kernel) ---
-template <bool LC>
+// ---- state access: plain vector, or sum_j c_j x_j formed on the fly ------------------------------------------------
+// SEQ (= EXACT grids): the combination is rounded like the op-by-op stage assembly of the RK driver (crd_fused.cuh);
+// otherwise a chain of fused multiply-adds in the order of lincomb_kernel.
+template <bool LC, bool SEQ>
 __device__ __forceinline__ double2 state2(const RhsArgs &a, long long p) {
   if constexpr (!LC) {
     return reinterpret_cast<const double2 *>(a.y)[p];
@@ -176,14 +179,13 @@ __device__ __forceinline__ double2 state2(const RhsArgs &a, long long p) {
 #pragma unroll
     for (int j = 0; j < kMaxLc; ++j)
       v[j] = (j < a.nlc) ? reinterpret_cast<const double2 *>(a.lc_x[j])[p] : make_double2(0.0, 0.0);
-    double2 s = make_double2(a.lc_c[0] * v[0].x, a.lc_c[0] * v[0].y);
+    double vx[kMaxLc], vy[kMaxLc];
 #pragma unroll
-    for (int j = 1; j < kMaxLc; ++j)
-      if (j < a.nlc) { s.x = fma(a.lc_c[j], v[j].x, s.x); s.y = fma(a.lc_c[j], v[j].y, s.y); }
-    return s;
+    for (int j = 0; j < kMaxLc; ++j) { vx[j] = v[j].x; vy[j] = v[j].y; }
+    return make_double2(lc_value<SEQ, kMaxLc>(a.lc_c, vx, a.nlc), lc_value<SEQ, kMaxLc>(a.lc_c, vy, a.nlc));
   }
 }
-template <bool LC>
+template <bool LC, bool SEQ>
 __device__ __forceinline__ double stateu(const RhsArgs &a, long long p) {
   if constexpr (!LC) {
     return a.y[2 * p];
@@ -191,18 +193,14 @@ __device__ __forceinline__ double stateu(const RhsArgs &a, long long p) {
     double v[kMaxLc];
 #pragma unroll
     for (int j = 0; j < kMaxLc; ++j) v[j] = (j < a.nlc) ? a.lc_x[j][2 * p] : 0.0;
-    double s = a.lc_c[0] * v[0];
-#pragma unroll
-    for (int j = 1; j < kMaxLc; ++j)
-      if (j < a.nlc) s = fma(a.lc_c[j], v[j], s);
-    return s;
+    return lc_value<SEQ, kMaxLc>(a.lc_c, v, a.nlc);
   }
 }
 // u of the row below / above the launch's rows at column i
-template <bool LC>
+template <bool LC, bool SEQ>
 __device__ __forceinline__ double ghost_u(const RhsArgs &a, const double *ptr, long long off, long long i) {
   if (!LC || ptr) return ptr[2 * i];
-  return stateu<true>(a, off + i);
+  return stateu<true, SEQ>(a, off + i);
 }
 
 }  // namespace

@@ -80,7 +80,7 @@ int check_flag(void *flagvalue, const std::string &funcname, int opt) {
 struct Shared {
   pthread_barrier_t bar;
   unsigned char handle[kMaxRanks][CRD_HALO_HANDLE_BYTES];
-  double red[kMaxRanks][8];
+  double red[kMaxRanks][3 * kMaxRanks];
   int failed;
 };
 Shared *g_shm = nullptr;
@@ -88,7 +88,7 @@ int g_rank = 0, g_nranks = 1;
 
 int shm_allreduce(double *vals, int n, int op, void *) {
   if (g_nranks == 1) return 0;
-  if (n > 8) return -1;
+  if (n > 3 * kMaxRanks) return -1;
   for (int i = 0; i < n; ++i) g_shm->red[g_rank][i] = vals[i];
   pthread_barrier_wait(&g_shm->bar);
   for (int i = 0; i < n; ++i) {
@@ -310,7 +310,7 @@ int run(const Config &c, int rank, int nranks) {
   if (check_flag(&flag, "ARKodeSetUserData", 1)) return 1;
   flag = ARKodeSetMaxNumSteps(arkode_mem, 200000);
   if (check_flag(&flag, "ARKodeSetMaxNumSteps", 1)) return (1);
-  if (c.fused) crd_ARKodeSetFusedOps(arkode_mem, crd_nv_fused_ops());
+  if (c.fused) crd_ARKodeSetFusedOps(arkode_mem, crd_nv_fused_ops_for(grid));   // EXACT grid: the bits of the op-by-op sequence
   crd_ARKodeSetReuseFirstStage(arkode_mem, c.reuse);
   crd_ARKodeSetResident(arkode_mem, c.resident);
 

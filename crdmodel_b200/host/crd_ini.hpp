@@ -1,6 +1,8 @@
 // crd_ini.hpp — the ini reader of the host drivers.  Same file format and the same lookup contract as the
 // reference's Boost.PropertyTree use (src/FHNmodel_torus.cpp:158-174): [Section] headers, key = value,
-// '#' / ';' comment lines, get<T>("Section.key") throws when the key is missing or does not convert.
+// '#' / ';' comment lines, get<T>("Section.key") throws when the key is missing or when the WHOLE value does not convert
+// (Boost's stream translator: `400abc` or `1e3` for an int is an error, not 400 / 1), a key defined twice in a section
+// is an error (Boost: "duplicate key name").
 #pragma once
 #include <fstream>
 #include <map>
@@ -27,7 +29,9 @@ class Ini {
       }
       const size_t eq = line.find('=');
       if (eq == std::string::npos) throw std::runtime_error(path + ": '=' character not found in line");
-      kv_[section.empty() ? trim(line.substr(0, eq)) : section + "." + trim(line.substr(0, eq))] = trim(line.substr(eq + 1));
+      const std::string key = section.empty() ? trim(line.substr(0, eq)) : section + "." + trim(line.substr(0, eq));
+      if (kv_.count(key)) throw std::runtime_error(path + ": duplicate key name (" + key + ")");
+      kv_[key] = trim(line.substr(eq + 1));
     }
   }
 
@@ -39,7 +43,7 @@ class Ini {
     std::istringstream is(it->second);
     T v{};
     is >> v;
-    if (is.fail()) throw std::runtime_error("conversion of data to type failed (" + key + ")");
+    if (is.fail() || !(is >> std::ws).eof()) throw std::runtime_error("conversion of data to type failed (" + key + ")");
     return v;
   }
   template <class T> T get(const std::string &key, const T &fallback) const { return has(key) ? get<T>(key) : fallback; }

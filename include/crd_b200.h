@@ -84,6 +84,15 @@ int crd_ctx_set_comm(crd_ctx *ctx, int rank, int nranks, crd_allreduce_fn fn, vo
 void *crd_ctx_stream(crd_ctx *ctx);
 int crd_ctx_device(crd_ctx *ctx);
 int crd_ctx_sync(crd_ctx *ctx);
+/* Device-side failures.  The only one: on a phi-split grid a neighbour's boundary rows did not arrive within the halo
+ * timeout (default 30 s; CRD_HALO_TIMEOUT_MS in the environment, or this call), i.e. a rank died or stalled — the situation in
+ * which the reference's MPI_Wait (src/FHNmodel_torus.cpp:904-946) would hang.  The evaluation that ran with stale rows is
+ * reported at the next point the host waits for the stream (every reduction, host copy, crd_ctx_sync): that call fails, and
+ * from then on EVERY entry point of the context fails (crd_f returns -1, so ARKode ends with ARK_RHSFUNC_FAIL) until
+ * crd_ctx_clear_error.  crd_ctx_failed: 0, or the device's error code. */
+int crd_ctx_set_halo_timeout(crd_ctx *ctx, double milliseconds);
+int crd_ctx_failed(crd_ctx *ctx);
+int crd_ctx_clear_error(crd_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t crd_ctx_launch_count(crd_ctx *ctx);
 /* device-side elapsed time between two points of the context's stream (CUDA events) */
@@ -138,7 +147,10 @@ int crd_rhs_host(crd_grid *g, double t, const double *y_host, double *ydot_host)
  * or -1 if the evaluation could not be issued (the reference returns -1 when Exchange fails, :522). */
 int crd_f(realtype t, N_Vector y, N_Vector ydot, void *user_data);
 /* ydot = f(t, sum_j c[j]*X[j]), n <= 5, without materialising the combination: the explicit RK stage assembly
- * (ARKode's N_VLinearSum chain before each stage, inside ARKode() :423) fused into the evaluation. */
+ * (ARKode's N_VLinearSum chain before each stage, inside ARKode() :423) fused into the evaluation.  Rounding of the
+ * combination: CRD_ARITH_FAST grids form c[0]*X[0] and add the other terms by fused multiply-adds in index order;
+ * CRD_ARITH_EXACT grids form it like the op-by-op stage assembly, s = c[1]*X[1] + 0, s = c[j]*X[j] + s (j = 2..),
+ * state = c[0]*X[0] + s, every product and sum rounded separately. */
 int crd_rhs_lincomb(crd_grid *g, double t, int n, const double *c, const double *const *X_dev, double *ydot_dev);
 int crd_f_lincomb(realtype t, int n, const realtype *c, N_Vector *X, N_Vector ydot, void *user_data);
 /* The last stage of a 5-stage explicit RK step fused with the step finish (ARKode's stage evaluation + arkComputeSolutions
@@ -186,6 +198,22 @@ typedef struct crd_ic_params {
 } crd_ic_params;
 int crd_fill_initial_conditions(crd_grid *g, const crd_ic_params *ic, double *y_dev);
 
+/* ---- output snapshots ----------------------------------------------------------------------------- */
+/* What main() does after every ARKode() call — walk the state's host array and fprintf variable 0 (and 1 when
+ * includeAllVars), src/FHNmodel_torus.cpp:393-410,438-455 — without stalling the time loop: crd_snapshot_begin ENQUEUES an
+ * output of the interleaved state as it is at this point of the context's stream (a small gather kernel into contiguous
+ * per-variable arrays, then an asynchronous device-to-host copy into one of `nslots` page-locked buffers on a side stream)
+ * and returns at once; a consumer thread calls crd_snapshot_wait (blocks until that copy has landed), reads the values and
+ * gives the buffer back with crd_snapshot_release.  nvars = 1 captures variable 0 only (8 instead of 16 B/point over PCIe).
+ * crd_snapshot_begin returns the slot (>= 0), -1 on failure, -2 when every slot is still held (release one and call again).
+ * begin / destroy: the context's thread; wait: any one consumer thread; release: either. */
+typedef struct crd_snapshot crd_snapshot;
+crd_snapshot *crd_snapshot_create(crd_ctx *ctx, int64_t npoints, int nvars, int nslots);
+void crd_snapshot_destroy(crd_snapshot *s);
+int crd_snapshot_begin(crd_snapshot *s, const double *y_dev);
+int crd_snapshot_wait(crd_snapshot *s, int slot, const double **var0, const double **var1);
+int crd_snapshot_release(crd_snapshot *s, int slot);
+
 /* ---- device-resident N_Vector ------------------------------------------------------------------ */
 N_Vector N_VNew_Crd(crd_ctx *ctx, long int local_length, long int global_length);
 N_Vector N_VNewEmpty_Crd(crd_ctx *ctx, long int local_length, long int global_length);
@@ -230,8 +258,24 @@ realtype N_VMinQuotient_Crd(N_Vector num, N_Vector denom);
 int N_VLinearCombination_Crd(int n, const realtype *c, N_Vector *X, N_Vector z);
 int N_VErkFinish_Crd(int s, const realtype *hb, const realtype *hd, N_Vector yn, N_Vector *F, N_Vector ynew,
                      realtype rtol, realtype atol, realtype out[2]);
-const crd_fused_ops *crd_nv_fused_ops(void);        /* lincomb + erk_finish + rhs_lincomb */
-const crd_fused_ops *crd_nv_fused_vector_ops(void); /* lincomb + erk_finish only (stage states are materialised) */
+/* the same step finish with the bits of the op-by-op sequence: separately rounded chains, IEEE error weights, the error sum
+ * accumulated in double-double (order-independent) */
+int N_VErkFinishSeq_Crd(int s, const realtype *hb, const realtype *hd, N_Vector yn, N_Vector *F, N_Vector ynew,
+                        realtype rtol, realtype atol, realtype out[2]);
+/* Tables of fused operations for crd_ARKodeSetFusedOps (crd_ark.h).
+ *   crd_nv_fused_ops / crd_nv_fused_vector_ops: chains of fused multiply-adds, approximate reciprocals for the error weights
+ *     (the arithmetic that goes with CRD_ARITH_FAST grids).
+ *   crd_nv_fused_ops_exact / crd_nv_fused_vector_ops_exact: every fused entry reproduces, bit for bit, what the op-by-op
+ *     sequence of N_Vector operations computes (stage assembly, solution, error estimate, error weights), and the error norm is
+ *     summed in double-double so that it does not depend on the order of summation: with a CRD_ARITH_EXACT grid the fused loop,
+ *     the op-by-op loop, any phi split and the CPU checker take the same steps and produce the same trajectory bit for bit.
+ *   crd_nv_fused_ops_for(grid): the table that matches the grid's arithmetic.
+ * "vector_ops": stage states are materialised (no rhs_lincomb / rhs_lincomb_finish / erk_evolve). */
+const crd_fused_ops *crd_nv_fused_ops(void);
+const crd_fused_ops *crd_nv_fused_vector_ops(void);
+const crd_fused_ops *crd_nv_fused_ops_exact(void);
+const crd_fused_ops *crd_nv_fused_vector_ops_exact(void);
+const crd_fused_ops *crd_nv_fused_ops_for(const crd_grid *g);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,14 @@
  * sqrt(sum_global((x_i w_i)^2) / N_global).  PARITY UNPINNED against SUNDIALS itself: the reference
  * ships no golden vectors for these ops; they are pinned against closed-form numpy results in
  * tests/test_oracle_nvector.py.
+ *
+ * One deliberate refinement: the weighted square sums (N_VWrmsNorm, N_VWrmsNormMask, N_VWL2Norm) add the terms
+ * RN(RN(x_i w_i)^2) — each rounded exactly like nvector_parallel's loop — EXACTLY (Shewchuk's growing expansion, as Python's
+ * math.fsum), gather the ranks' (hi, lo) pairs and round once, instead of accumulating in index order.  The result is the
+ * correctly rounded sum, independent of the order of summation and of the decomposition, which is also what the device
+ * reductions deliver (double-double accumulation): the integrator's error norm, hence its step sequence, is then the
+ * same on both sides bit for bit.  CRD_ORACLE_PLAIN_SUM=1 restores the serial `sum += prodi*prodi` (differs in the last
+ * bits only).
  */
 #include <float.h>
 #include <math.h>
@@ -27,6 +35,70 @@ static double allreduce(double d, int op, MPI_Comm comm) {
   double out;
   MPI_Allreduce(&d, &out, 1, MPI_DOUBLE, op, comm);
   return out;
+}
+
+/* ---- exact accumulation of doubles (Shewchuk 1997, "msum"): the partials are a non-overlapping expansion of the sum ---- */
+typedef struct { double p[64]; int n; } exact_acc;
+static void xs_add(exact_acc *a, double x) {
+  int i = 0, j;
+  for (j = 0; j < a->n; j++) {
+    double y = a->p[j], hi, lo;
+    if (fabs(x) < fabs(y)) { double t = x; x = y; y = t; }
+    hi = x + y;
+    lo = y - (hi - x);
+    if (lo != 0.0) a->p[i++] = lo;
+    x = hi;
+  }
+  a->p[i++] = x;
+  a->n = i;
+}
+/* (hi, lo): hi = the correctly rounded sum (round-half-even fix-up as in CPython's math.fsum), lo = what the next partials add */
+static void xs_result(const exact_acc *a, double *hi_out, double *lo_out) {
+  int n = a->n;
+  double hi = 0.0, lo = 0.0;
+  if (n > 0) {
+    hi = a->p[--n];
+    while (n > 0) {
+      double x = hi, y = a->p[--n];
+      hi = x + y;
+      lo = y - (hi - x);
+      if (lo != 0.0) break;
+    }
+    if (n > 0 && ((lo < 0.0 && a->p[n - 1] < 0.0) || (lo > 0.0 && a->p[n - 1] > 0.0))) {
+      double y = lo * 2.0, x = hi + y, yr = x - hi;
+      if (y == yr) { hi = x; lo = 0.0; }   /* exactly half-way and the tail pushes it over */
+    }
+    /* remainder below hi, for merging with other ranks' sums */
+    { double rest = lo; int k; for (k = n - 1; k >= 0; k--) rest += a->p[k]; lo = rest; }
+  }
+  *hi_out = hi; *lo_out = lo;
+}
+static int plain_sum(void) {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("CRD_ORACLE_PLAIN_SUM"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
+/* global value of a local exact sum: the ranks' (hi, lo) pairs gathered (a SUM over a vector that is zero except for the
+ * rank's own slots is exact) and added in rank order in double-double, rounded once */
+static double allreduce_exact(const exact_acc *a, MPI_Comm comm) {
+  int size = 1, rank = 0, r;
+  double hi, lo;
+  xs_result(a, &hi, &lo);
+  MPI_Comm_size(comm, &size);
+  if (size <= 1) return hi + lo;
+  MPI_Comm_rank(comm, &rank);
+  {
+    double *in = (double *)calloc((size_t)4 * size, sizeof(double)), *out = in + 2 * size;
+    exact_acc t;
+    double res, rl;
+    in[2 * rank] = hi; in[2 * rank + 1] = lo;
+    MPI_Allreduce(in, out, 2 * size, MPI_DOUBLE, MPI_SUM, comm);
+    t.n = 0;
+    for (r = 0; r < 2 * size; r++) xs_add(&t, out[r]);
+    xs_result(&t, &res, &rl);
+    free(in);
+    return res;
+  }
 }
 
 static N_Vector nvh_clone(N_Vector w);
@@ -125,12 +197,22 @@ static realtype nvh_maxnorm(N_Vector x) {
 static realtype nvh_wrmsnorm(N_Vector x, N_Vector w) {
   long int i, N = NV_LOCLENGTH_P(x), Ng = NV_GLOBLENGTH_P(x);
   realtype sum = ZERO, prodi, *xd = NV_DATA_P(x), *wd = NV_DATA_P(w);
+  if (!plain_sum()) {
+    exact_acc a; a.n = 0;
+    for (i = 0; i < N; i++) { prodi = xd[i] * wd[i]; xs_add(&a, prodi * prodi); }
+    return sqrt(allreduce_exact(&a, NV_COMM_P(x)) / Ng);
+  }
   for (i = 0; i < N; i++) { prodi = xd[i] * wd[i]; sum += prodi * prodi; }
   return sqrt(allreduce(sum, MPI_SUM, NV_COMM_P(x)) / Ng);
 }
 static realtype nvh_wrmsnormmask(N_Vector x, N_Vector w, N_Vector id) {
   long int i, N = NV_LOCLENGTH_P(x), Ng = NV_GLOBLENGTH_P(x);
   realtype sum = ZERO, prodi, *xd = NV_DATA_P(x), *wd = NV_DATA_P(w), *idd = NV_DATA_P(id);
+  if (!plain_sum()) {
+    exact_acc a; a.n = 0;
+    for (i = 0; i < N; i++) if (idd[i] > ZERO) { prodi = xd[i] * wd[i]; xs_add(&a, prodi * prodi); }
+    return sqrt(allreduce_exact(&a, NV_COMM_P(x)) / Ng);
+  }
   for (i = 0; i < N; i++) if (idd[i] > ZERO) { prodi = xd[i] * wd[i]; sum += prodi * prodi; }
   return sqrt(allreduce(sum, MPI_SUM, NV_COMM_P(x)) / Ng);
 }
@@ -143,6 +225,11 @@ static realtype nvh_min(N_Vector x) {
 static realtype nvh_wl2norm(N_Vector x, N_Vector w) {
   long int i, N = NV_LOCLENGTH_P(x);
   realtype sum = ZERO, prodi, *xd = NV_DATA_P(x), *wd = NV_DATA_P(w);
+  if (!plain_sum()) {
+    exact_acc a; a.n = 0;
+    for (i = 0; i < N; i++) { prodi = xd[i] * wd[i]; xs_add(&a, prodi * prodi); }
+    return sqrt(allreduce_exact(&a, NV_COMM_P(x)));
+  }
   for (i = 0; i < N; i++) { prodi = xd[i] * wd[i]; sum += prodi * prodi; }
   return sqrt(allreduce(sum, MPI_SUM, NV_COMM_P(x)));
 }

@@ -21,6 +21,14 @@ int main(int argc, char **argv) {
   threw = false;
   try { pt.get<int>("Parameters.word"); } catch (const std::runtime_error &e) { threw = std::strstr(e.what(), "conversion") != nullptr; }
   CHECK(threw);
+  // the whole value must convert (Boost's translator): no silent 1e3 -> 1 or 0.4abc -> 0.4
+  for (const char *k : {"Parameters.sci_int", "Parameters.trailing", "Parameters.two_numbers"}) {
+    threw = false;
+    try { (k[11] == 's') ? (void)pt.get<int>(k) : (void)pt.get<double>(k); } catch (const std::runtime_error &e) { threw = std::strstr(e.what(), "conversion") != nullptr; }
+    CHECK(threw);
+  }
+  CHECK(pt.get<double>("Parameters.sci_int") == 1000.0);     // as a double it is fine
+  CHECK(pt.get<double>("Parameters.padded") == 2.5);         // surrounding blanks are not part of the value
   threw = false;
   try { crd::Ini missing("/nonexistent/file.ini"); } catch (const std::runtime_error &) { threw = true; }
   CHECK(threw);

@@ -15,6 +15,10 @@ beta=1.25
 tFinal = 50
 comment_like = a # b ; c
 word = abc
+sci_int = 1e3
+trailing = 0.4abc
+two_numbers = 1 2
+padded =    2.5   
 
 [System]
 varyBeta = 1
@@ -33,3 +37,7 @@ def test_ini_reader_contract(tmp_path):
     bad.write_text("[Parameters\nx = 1\n")
     r = subprocess.run([exe, str(bad)], capture_output=True, text=True)
     assert r.returncode != 0          # unmatched '[' is an error, like Boost's ini_parser_error
+    dup = tmp_path / "dup.ini"
+    dup.write_text(INI.replace("tFinal = 50", "tFinal = 50\ndiffusion = 0.5"))
+    r = subprocess.run([exe, str(dup)], capture_output=True, text=True)
+    assert r.returncode != 0          # Boost: "duplicate key name"

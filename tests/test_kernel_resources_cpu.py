@@ -41,7 +41,7 @@ def test_register_budgets_of_the_default_kernels(usage, model, exact):
         assert sig in usage, "kernel not in the library: " + sig
         return usage[sig][1]
     # headline: tiled kernel, 256 threads, 3 CTAs/SM -> 65536 / 768 = 85 -> 80
-    assert regs("rhs_tile_kernel<%d, %s, 256, 16, 3, false, false, 3, false>" % (model, exact)) <= 80
+    assert regs("rhs_tile_kernel<%d, %s, 256, 16, 3, false, false, 3>" % (model, exact)) <= 80
     # streaming kernel, 288 threads: 3 CTAs/SM -> 72 registers (2- and 3-vector stages, last stage + finish)
     for nv, rb, fin in ((2, 2, 0), (3, 2, 0), (5, 1, 2)):
         assert regs("rhs_stream_kernel<%d, %s, %d, false, %d, %d, 3>" % (model, exact, nv, rb, fin)) <= 72
@@ -58,7 +58,7 @@ def test_resident_loop_fits_one_cta_of_512_threads_per_sm(usage):
 
 def test_headline_kernel_uses_tma_bulk_copies_and_mbarriers(usage, crd):
     from crdmodel_b200 import build as B
-    mangled = usage["rhs_tile_kernel<0, true, 256, 16, 3, false, false, 3, false>"][0]
+    mangled = usage["rhs_tile_kernel<0, true, 256, 16, 3, false, false, 3>"][0]
     sass = subprocess.run([CUOBJDUMP, "-sass", "-fun", mangled, B.LIB], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass, "no TMA bulk copy in the headline kernel"
     assert "SYNCS" in sass, "no mbarrier operations in the headline kernel"

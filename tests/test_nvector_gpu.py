@@ -67,12 +67,14 @@ def test_reductions(crd, ctx, n):
         assert abs(got - want) <= tol * scale + 1e-300, (got, want)
     close(crd.N_VDotProd(X, Y), math.fsum(x * y), math.fsum(np.abs(x * y)))
     close(crd.N_VL1Norm(X), math.fsum(np.abs(x)), math.fsum(np.abs(x)))
+    # weighted square sums: every term rounded like nvector_parallel's loop, the sum accumulated in double-double and rounded
+    # once -> the exactly rounded sum (math.fsum), whatever the grouping of the terms over threads, blocks and ranks
     s2 = math.fsum((x * w) ** 2)
-    close(crd.N_VWrmsNorm(X, W), math.sqrt(s2 / n), math.sqrt(s2 / n))
-    close(crd.N_VWL2Norm(X, W), math.sqrt(s2), math.sqrt(s2))
+    assert crd.N_VWrmsNorm(X, W) == math.sqrt(s2 / n)
+    assert crd.N_VWL2Norm(X, W) == math.sqrt(s2)
     idm = (rng.random(n) > 0.5).astype(float)
     sm = math.fsum(((x * w) ** 2)[idm > 0])
-    close(crd.N_VWrmsNormMask(X, W, crd.NVector.from_numpy(ctx, idm)), math.sqrt(sm / n), math.sqrt(s2 / n))
+    assert crd.N_VWrmsNormMask(X, W, crd.NVector.from_numpy(ctx, idm)) == math.sqrt(sm / n)
     assert crd.N_VMaxNorm(X) == np.abs(x).max()
     assert crd.N_VMin(X) == x.min()
     assert crd.N_VMinQuotient(X, W) == (x / w).min()
@@ -126,6 +128,25 @@ def test_fused_ops(crd, ctx, n):
     we2 = math.fsum((err / (rtol * np.abs(yn) + atol)) ** 2)
     wy2 = math.fsum((ynew / (rtol * np.abs(ynew) + atol)) ** 2)
     assert abs(e2 - we2) <= 1e-10 * we2 and abs(y2 - wy2) <= 1e-10 * wy2
+    # the same finish with the bits of the op-by-op sequence (N_VErkFinishSeq_Crd): the N_VLinearSum chains of
+    # compute_solution(), the ewt chain abs / scale / addconst / inv, N_VWrmsNorm's terms, an exactly rounded sum
+    Z2 = crd.NVector(ctx, n)
+    e2x, y2x = crd.N_VErkFinish(list(hb), list(hd), Yn, V[1:6], Z2, rtol, atol, exact=True)
+    ycur, tempv = yn.copy(), np.zeros(n)
+    for j in range(5):
+        if hb[j] != 0.0:
+            ycur = hb[j] * F[j] + ycur
+        tempv = hd[j] * F[j] + tempv
+    assert Z2.to_numpy().tobytes() == ycur.tobytes()
+    assert e2x == math.fsum((tempv * (1.0 / (rtol * np.abs(yn) + atol))) ** 2)
+    assert abs(y2x - wy2) <= 1e-10 * wy2
+    # and through the vector operations themselves, one by one
+    T, Ew = crd.NVector(ctx, n), crd.NVector(ctx, n)
+    crd.N_VConst(0.0, T)
+    for j in range(5):
+        crd.N_VLinearSum(float(hd[j]), V[1 + j], 1.0, T, T)
+    crd.N_VAbs(Yn, Ew); crd.N_VScale(rtol, Ew, Ew); crd.N_VAddConst(Ew, atol, Ew); crd.N_VInv(Ew, Ew)
+    assert crd.N_VWrmsNorm(T, Ew) == math.sqrt(e2x / n)
 
 
 def test_host_mirror_roundtrip(crd, ctx):

@@ -14,4 +14,4 @@ def test_async_writer_bytes_equal_fprintf(tmp_path):
     a, b, r = (str(tmp_path / n) for n in ("a.txt", "b.txt", "ref.txt"))
     subprocess.run([exe, a, b, r], check=True)
     assert filecmp.cmp(a, r, shallow=False)
-    assert os.path.getsize(b) > 0 and sum(1 for _ in open(b)) == 2
+    assert os.path.getsize(b) > 0 and sum(1 for _ in open(b)) == 3
