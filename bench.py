@@ -465,6 +465,7 @@ def main():
     ctx = crd.Context(local_rank)
     if use_dist:
         ctx.set_comm(rank, world, cdist.make_allreduce(gloo))
+        cdist.comm_connect(ctx, rank, world, gloo)      # the integrator's norms are finished on the devices (mailboxes over NVLink)
     peaks, peaks_src = measured_peaks()
     sampler = ClockSampler(local_rank) if rank == 0 else None
 

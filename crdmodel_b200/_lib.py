@@ -46,6 +46,9 @@ SIGNATURES = {
     "crd_ctx_create": (P, [I, P]),
     "crd_ctx_destroy": (None, [P]),
     "crd_ctx_set_comm": (I, [P, I, I, ALLREDUCE_FN, P]),
+    "crd_ctx_comm_handle": (I, [P, C.c_char_p]),
+    "crd_ctx_comm_connect_ipc": (I, [P, I, I, C.c_char_p]),
+    "crd_ctx_comm_connect_local": (I, [P, I, I, C.POINTER(P)]),
     "crd_ctx_stream": (P, [P]),
     "crd_ctx_device": (I, [P]),
     "crd_ctx_sync": (I, [P]),

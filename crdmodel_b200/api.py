@@ -5,6 +5,7 @@ so tests read like the reference's own call sites (src/FHNmodel_torus.cpp:281,35
 Nothing here computes: every method is one call into libcrd_b200.so.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -44,9 +45,20 @@ class Context:
         self._h = check_ptr(lib().crd_ctx_create(device, stream), "crd_ctx_create")
         self._cb = None
         self.device = device
+        # everything created from this context (solvers, grids, vectors) is destroyed with it, in that order: the C objects
+        # hold a pointer to the context and must not outlive it whatever order Python finalises the wrappers in
+        self._children = weakref.WeakSet()
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     def close(self):
         if self._h:
+            kids = list(self._children)
+            for rank_ in (0, 1, 2):
+                for k in kids:
+                    if k._close_rank == rank_:
+                        k._release()
             lib().crd_ctx_destroy(self._h)
             self._h = None
 
@@ -68,6 +80,22 @@ class Context:
                 return -1
         self._cb = _lib.ALLREDUCE_FN(_cb)
         check(lib().crd_ctx_set_comm(self._h, rank, nranks, self._cb, None), "crd_ctx_set_comm")
+
+    def comm_handle(self):
+        """64-byte handle of this context's mailbox block for the device-side allreduce."""
+        buf = C.create_string_buffer(_lib.HALO_HANDLE_BYTES)
+        check(lib().crd_ctx_comm_handle(self._h, buf), "crd_ctx_comm_handle")
+        return buf.raw
+
+    def comm_connect_ipc(self, rank, nranks, handles):
+        """handles: every rank's comm_handle(), in rank order.  Reductions are finished on the device from then on."""
+        blob = b"".join(bytes(h) for h in handles)
+        check(lib().crd_ctx_comm_connect_ipc(self._h, rank, nranks, blob), "crd_ctx_comm_connect_ipc")
+
+    def comm_connect_local(self, rank, ctxs):
+        """The same for contexts of this process (any devices with peer access)."""
+        arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+        check(lib().crd_ctx_comm_connect_local(self._h, rank, len(ctxs), arr), "crd_ctx_comm_connect_local")
 
     def sync(self):
         check(lib().crd_ctx_sync(self._h), "crd_ctx_sync")
@@ -130,6 +158,12 @@ class NVector:
             g = local_length if global_length is None else global_length
             self.h = check_ptr(lib().N_VNew_Crd(ctx._h, local_length, g), "N_VNew_Crd")
         self.n = lib().N_VGetLocalLength_Crd(self.h)
+        ctx._adopt(self)
+
+    _close_rank = 2
+
+    def _release(self):
+        self.destroy()
 
     @classmethod
     def from_numpy(cls, ctx, a, global_length=None):
@@ -158,7 +192,8 @@ class NVector:
 
     def destroy(self):
         if self.h:
-            lib().N_VDestroy(self.h)
+            if self.ctx._h:                 # (a vector that outlived its context was released with it)
+                lib().N_VDestroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -223,10 +258,17 @@ class Grid:
         self.nyl = self.je - self.js + 1
         self.local_length = lib().crd_grid_local_length(self._h)
         self.global_length = lib().crd_grid_global_length(self._h)
+        ctx._adopt(self)
+
+    _close_rank = 1
+
+    def _release(self):
+        self.close()
 
     def close(self):
         if self._h:
-            lib().crd_grid_destroy(self._h)
+            if self.ctx._h:
+                lib().crd_grid_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -322,6 +364,7 @@ class ARKodeSolver:
         L = lib()
         self.grid, self.y = grid, y
         self.mem = C.c_void_p(check_ptr(L.ARKodeCreate(), "ARKodeCreate"))
+        grid.ctx._adopt(self)
         f = C.cast(L.crd_f, C.c_void_p)
         check(L.ARKodeInit(self.mem, f, None, t0, y.h), "ARKodeInit")
         check(L.ARKodeSStolerances(self.mem, rtol, atol), "ARKodeSStolerances")
@@ -349,6 +392,11 @@ class ARKodeSolver:
         # stage_finish: the last stage and the step finish in one pass over memory where the grid offers it (one GPU, large mesh)
         check(L.crd_ARKodeSetStageFinish(self.mem, 1 if stage_finish else 0), "crd_ARKodeSetStageFinish")
 
+    _close_rank = 0
+
+    def _release(self):
+        self.free()
+
     def set_init_step(self, h):
         check(lib().crd_ARKodeSetInitStep(self.mem, h), "crd_ARKodeSetInitStep")
 
@@ -374,7 +422,8 @@ class ARKodeSolver:
 
     def free(self):
         if self.mem:
-            lib().ARKodeFree(C.byref(self.mem))
+            if self.grid.ctx._h:
+                lib().ARKodeFree(C.byref(self.mem))
             self.mem = None
 
     def __del__(self):

@@ -37,6 +37,24 @@ constexpr int kRedThreads = 256;
 constexpr int kRedSlots = 4;         // values one reduction kernel can return
 constexpr int kMaxRanks = 64;        // ranks of a phi split (cross-rank sums gather one slot per rank)
 
+// Device-side allreduce of a few doubles across the ranks of a phi split (the MPI_Allreduce inside nvector_parallel's
+// reductions).  Every context owns a mailbox block in device memory (exported by CUDA IPC); a reduction's finishing block
+// stores its local values into EVERY rank's mailbox through the peer mappings (its own included), publishes a sequence
+// number per destination, waits until every rank's sequence number has arrived in its own block, and combines the values
+// in rank order — all ranks therefore compute the same bits, and no host takes part.  Mailboxes are double-buffered by the
+// parity of the sequence number (a rank can be at most one reduction ahead: it needs everybody's values to finish one).
+constexpr int kCommVals = 4;
+struct CommTab {
+  double *mail[kMaxRanks];               // rank r's block: double [2 parity][kMaxRanks source][kCommVals]
+  unsigned long long *flag[kMaxRanks];   // rank r's flags: [kMaxRanks source] sequence number of the last complete store
+  int rank, nranks;
+  long long timeout_ns;
+  int *err;
+};
+constexpr size_t kCommMailBytes = sizeof(double) * 2 * kMaxRanks * kCommVals;
+constexpr size_t kCommBlockBytes = kCommMailBytes + sizeof(unsigned long long) * kMaxRanks;
+enum { COMM_SUM_DD = 0, COMM_MAX = 1, COMM_MIN = 2 };   // SUM_DD: slots (hi, plain, lo): hi/lo merged in double-double, plain added
+
 }  // namespace crd
 
 struct crd_ctx {
@@ -59,6 +77,13 @@ struct crd_ctx {
   // error word written by device code (halo wait timeout); pinned, mapped
   int *err_host = nullptr;
   int *err_dev = nullptr;
+  // device-side allreduce (crd_ctx_comm_*): the local mailbox block, the table of everybody's, the reduction counter
+  char *comm_local = nullptr;
+  crd::CommTab *comm_tab = nullptr;       // device copy of the table
+  void *comm_peer[crd::kMaxRanks] = {};   // IPC mappings to close
+  bool dev_comm = false;
+  unsigned long long comm_seq = 0;
+  double *red_local = nullptr;            // device: a reduction's local result, input of the exchange
   // L2 flush scratch
   void *flush_buf = nullptr;
   size_t flush_bytes = 0;
@@ -93,6 +118,11 @@ inline int sync_stream(crd_ctx *c, const char *what) {
 // second value; the pairs are gathered through the allreduce hook (a SUM over a vector that is zero outside the rank's own
 // slots is exact) and merged in rank order, so all ranks — and any phi split — get the same bits.  Returns RN(hi + lo).
 int allreduce_dd(crd_ctx *c, double &hi, double &lo, double *plain);
+// Where a reduction kernel's finishing block writes: the mapped host result when the value is final (one rank, or the host
+// hook finishes it), device scratch when the device-side exchange follows.
+inline double *red_target(crd_ctx *c) { return c->dev_comm ? c->red_local : c->red_result_dev; }
+// the exchange as a launch of its own (n <= kCommVals values of red_local -> red_result); no-op unless dev_comm
+int launch_comm_exchange(crd_ctx *c, int op, int n);
 
 inline int check_launch(crd_ctx *c, const char *what) {
   c->launches++;

@@ -1,4 +1,5 @@
 // crd_ctx.cu — device context, memory helpers, timers, synthetic-state generator.
+#include <cstddef>
 #include <cstdlib>
 
 #include "crd_common.cuh"
@@ -13,7 +14,7 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 int allreduce_dd(crd_ctx *c, double &hi, double &lo, double *plain) {
-  if (c->nranks <= 1) return 0;
+  if (c->nranks <= 1 || c->dev_comm) return 0;   // one rank, or the device-side exchange has already made the values global
   if (c->nranks > kMaxRanks || !c->allreduce) { set_error("allreduce_dd: %d ranks without a usable allreduce hook", c->nranks); return -1; }
   double v[3 * kMaxRanks];
   const int n = 3 * c->nranks;
@@ -25,6 +26,23 @@ int allreduce_dd(crd_ctx *c, double &hi, double &lo, double *plain) {
   hi = h; lo = l;
   if (plain) *plain = p;
   return 0;
+}
+static __global__ void __launch_bounds__(64) comm_exchange_kernel(const CommTab *T, unsigned long long seq, int op, int n, const double *local, double *result) {
+  __shared__ double v[kCommVals];
+  if (threadIdx.x < kCommVals) v[threadIdx.x] = threadIdx.x < n ? local[threadIdx.x] : 0.0;
+  __syncthreads();
+  comm_allreduce_block(T, seq, op, kCommVals, v);   // every slot travels (zeros beyond n): nothing stale is ever combined
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kCommVals; ++i) result[i] = v[i];
+    __threadfence_system();
+  }
+}
+
+int launch_comm_exchange(crd_ctx *c, int op, int n) {
+  if (!c->dev_comm) return 0;
+  ++c->comm_seq;
+  comm_exchange_kernel<<<1, 64, 0, c->stream>>>(c->comm_tab, c->comm_seq, op, n, c->red_local, c->red_result_dev);
+  return check_launch(c, "comm_exchange_kernel");
 }
 }  // namespace crd
 
@@ -73,6 +91,10 @@ crd_ctx *crd_ctx_create(int device, void *stream) {
   CRD_CUDA_NULL(cudaMemset(c->red_ticket, 0, sizeof(unsigned int)));
   CRD_CUDA_NULL(cudaHostAlloc(&c->red_result_host, sizeof(double) * kRedSlots, cudaHostAllocMapped));
   CRD_CUDA_NULL(cudaHostGetDevicePointer(&c->red_result_dev, c->red_result_host, 0));
+  CRD_CUDA_NULL(cudaMalloc(&c->red_local, sizeof(double) * kRedSlots));
+  CRD_CUDA_NULL(cudaMalloc(&c->comm_local, kCommBlockBytes));
+  CRD_CUDA_NULL(cudaMemset(c->comm_local, 0, kCommBlockBytes));
+  CRD_CUDA_NULL(cudaMalloc(&c->comm_tab, sizeof(CommTab)));
   CRD_CUDA_NULL(cudaHostAlloc(&c->err_host, sizeof(int), cudaHostAllocMapped));
   *c->err_host = 0;
   CRD_CUDA_NULL(cudaHostGetDevicePointer(&c->err_dev, c->err_host, 0));
@@ -86,6 +108,11 @@ void crd_ctx_destroy(crd_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (c->comm_peer[r]) cudaIpcCloseMemHandle(c->comm_peer[r]);
+  cudaFree(c->comm_local);
+  cudaFree(c->comm_tab);
+  cudaFree(c->red_local);
   cudaFree(c->red_partial);
   cudaFree(c->red_ticket);
   cudaFreeHost(c->red_result_host);
@@ -114,9 +141,74 @@ int crd_ctx_sync(crd_ctx *c) {
   return sync_stream(c, "crd_ctx_sync") ? -2 : 0;
 }
 
+// ---- device-side allreduce: wiring ------------------------------------------------------------------------------------
+static int comm_install(crd_ctx *c, int rank, int nranks, char *const *blocks) {
+  CommTab T;
+  std::memset(&T, 0, sizeof T);
+  for (int r = 0; r < nranks; ++r) {
+    T.mail[r] = (double *)blocks[r];
+    T.flag[r] = (unsigned long long *)(blocks[r] + kCommMailBytes);
+  }
+  T.rank = rank; T.nranks = nranks; T.timeout_ns = c->halo_timeout_ns; T.err = c->err_dev;
+  CRD_CUDA(cudaMemcpy(c->comm_tab, &T, sizeof T, cudaMemcpyHostToDevice));
+  c->rank = rank; c->nranks = nranks;
+  c->dev_comm = nranks > 1;
+  c->comm_seq = 0;
+  return 0;
+}
+
+int crd_ctx_comm_handle(crd_ctx *c, unsigned char handle[CRD_HALO_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == CRD_HALO_HANDLE_BYTES, "handle size");
+  if (!c || !handle) return -1;
+  if (use(c)) return -1;
+  cudaIpcMemHandle_t h;
+  CRD_CUDA(cudaIpcGetMemHandle(&h, c->comm_local));
+  std::memcpy(handle, &h, sizeof h);
+  return 0;
+}
+
+int crd_ctx_comm_connect_ipc(crd_ctx *c, int rank, int nranks, const unsigned char *handles) {
+  if (!c || !handles || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) { set_error("crd_ctx_comm_connect_ipc: bad arguments"); return -1; }
+  if (use(c)) return -1;
+  char *blocks[kMaxRanks];
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) { blocks[r] = c->comm_local; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + (size_t)r * CRD_HALO_HANDLE_BYTES, sizeof h);
+    void *p = nullptr;
+    CRD_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->comm_peer[r] = p;
+    blocks[r] = (char *)p;
+  }
+  return comm_install(c, rank, nranks, blocks);
+}
+
+int crd_ctx_comm_connect_local(crd_ctx *c, int rank, int nranks, crd_ctx *const *all) {
+  if (!c || !all || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks || all[rank] != c) { set_error("crd_ctx_comm_connect_local: bad arguments"); return -1; }
+  if (use(c)) return -1;
+  char *blocks[kMaxRanks];
+  for (int r = 0; r < nranks; ++r) {
+    if (!all[r]) { set_error("crd_ctx_comm_connect_local: null context"); return -1; }
+    if (all[r]->device != c->device) {
+      int can = 0;
+      CRD_CUDA(cudaDeviceCanAccessPeer(&can, c->device, all[r]->device));
+      if (!can) { set_error("device %d cannot access device %d", c->device, all[r]->device); return -1; }
+      cudaError_t e = cudaDeviceEnablePeerAccess(all[r]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); return -1; }
+      cudaGetLastError();
+    }
+    blocks[r] = all[r]->comm_local;
+  }
+  return comm_install(c, rank, nranks, blocks);
+}
+
 int crd_ctx_set_halo_timeout(crd_ctx *c, double milliseconds) {
   if (!c || !(milliseconds > 0.0)) { set_error("crd_ctx_set_halo_timeout: bad arguments"); return -1; }
   c->halo_timeout_ns = (long long)(milliseconds * 1.0e6);
+  if (c->dev_comm) {   // the exchange's table carries a copy
+    if (use(c)) return -1;
+    CRD_CUDA(cudaMemcpy((char *)c->comm_tab + offsetof(CommTab, timeout_ns), &c->halo_timeout_ns, sizeof(long long), cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 

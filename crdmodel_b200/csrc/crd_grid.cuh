@@ -38,6 +38,25 @@ struct StateRef {
   double c[kMaxLc] = {};
 };
 
+// Halo exchange folded into an evaluation's own launch (phi-split grids).  The boundary rows travel by plain stores through
+// peer-mapped memory; ordering is per STRIP of kHaloStrip theta columns: the CTA that has written a strip of a neighbour's
+// ghost row release-stores the evaluation's epoch into that strip's flag over there, and whoever needs a ghost-row strip
+// acquires its own flag first.  A launch may push (its first CTAs do, before anything else), wait (the tiles / row segments
+// that touch a ghost row do, and they are scheduled last), both, or neither.
+constexpr int kHaloStrip = 256;
+struct HaloSync {
+  double *push_prev = nullptr;                    // prev rank's north ghost row of this epoch: receives this slab's row 0
+  double *push_next = nullptr;                    // next rank's south ghost row: receives this slab's last row
+  unsigned long long *flag_prev = nullptr;        // their per-strip flags
+  unsigned long long *flag_next = nullptr;
+  const unsigned long long *wait_south = nullptr; // this grid's per-strip flags: acquire before the south / north ghost row is read
+  const unsigned long long *wait_north = nullptr;
+  unsigned long long epoch = 0;
+  long long timeout_ns = 0;
+  int *err = nullptr;                             // mapped host word: a wait gave up (the launch still completes, with stale rows)
+  int edge_last = 0;                              // schedule the work that touches ghost rows last
+};
+
 struct RhsArgs {
   const double *y;
   double *ydot;
@@ -57,16 +76,20 @@ struct RhsArgs {
   int div_shift;         // >= 0: work item / nx by multiply-shift (set at launch)
   unsigned div_magic;
   RhsConst k;
+  HaloSync hs;
 };
 
 // ghost block, one per grid, cudaMalloc'd so it can be exported with cudaIpcGetMemHandle:
-//   double ghost[2 parity][2 side][nx][2]  side 0 = south (row js-1), side 1 = north (row je+1); whole (u,v) rows
-//   unsigned long long flag[2 side]        epoch of the last complete push, 128 B apart
+//   double ghost[2 parity][2 side][nx][2]        side 0 = south (row js-1), side 1 = north (row je+1); whole (u,v) rows
+//   unsigned long long flag[2 side][nstrips]     per strip of kHaloStrip columns: epoch of the last complete push
 struct HaloLayout {
   long long nx;
+  __host__ __device__ long long nstrips() const { return (nx + kHaloStrip - 1) / kHaloStrip; }
   __host__ __device__ size_t ghost_off(int parity, int side) const { return (size_t)(parity * 2 + side) * (size_t)nx * 2 * sizeof(double); }
-  __host__ __device__ size_t flag_off(int side) const { return (size_t)4 * (size_t)nx * 2 * sizeof(double) + 128 + (size_t)side * 128; }
-  __host__ __device__ size_t bytes() const { return flag_off(1) + 128; }
+  __host__ __device__ size_t flag_off(int side) const {
+    return (size_t)4 * (size_t)nx * 2 * sizeof(double) + 128 + (size_t)side * (((size_t)nstrips() * 8 + 127) / 128 * 128);
+  }
+  __host__ __device__ size_t bytes() const { return flag_off(2); }
 };
 
 }  // namespace crd
@@ -84,7 +107,6 @@ struct crd_grid {
   char *halo_prev = nullptr, *halo_next = nullptr;  // peer-mapped (or local) ghost blocks of the neighbours
   bool prev_ipc = false, next_ipc = false;
   bool connected = false;
-  unsigned long long *push_ticket = nullptr;
   unsigned long long epoch = 0;      // epoch of the last post
   unsigned long long computed = 0;   // epoch of the last compute
   int64_t rhs_count = 0;
@@ -97,10 +119,9 @@ struct crd_grid {
   unsigned long long *res_bar = nullptr;
   double *res_partial = nullptr;
   void *res_out_host = nullptr, *res_out_dev = nullptr;
-  // overlap of the halo exchange with the interior rows (auxiliary stream)
-  bool overlap = true, split = false;
-  cudaStream_t s_aux = nullptr;
-  cudaEvent_t ev_y = nullptr, ev_b = nullptr;
+  // true (default): the exchange rides inside the evaluation's own launch where the kernel supports it (the tiled and the
+  // streaming kernels); false: always the separate push / wait launches
+  bool overlap = true;
   // crd_rhs_host staging
   double *stage_y = nullptr, *stage_ydot = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;

@@ -264,12 +264,13 @@ double reduce(crd_ctx *c, M m, const double *x, const double *y, const double *z
   if (n > 0) {
     unsigned int blocks = grid_for((n + 1) / 2, c->sms);
     if (blocks > (unsigned)kRedBlocks) blocks = kRedBlocks;
-    red_kernel<OP, M, HAS_Y, HAS_Z><<<blocks, kRedThreads, 0, c->stream>>>(m, x, y, z, n, c->red_partial, c->red_ticket, c->red_result_dev);
+    red_kernel<OP, M, HAS_Y, HAS_Z><<<blocks, kRedThreads, 0, c->stream>>>(m, x, y, z, n, c->red_partial, c->red_ticket, red_target(c));
     if (check_launch(c, name)) return NAN;
+    if (launch_comm_exchange(c, OP == OP_SUM ? COMM_SUM_DD : (OP == OP_MAX ? COMM_MAX : COMM_MIN), 1)) return NAN;
     if (sync_stream(c, name)) return NAN;
     v = c->red_result_host[0];
   }
-  if (c->nranks > 1) {
+  if (c->nranks > 1 && !c->dev_comm) {
     const int op = OP == OP_SUM ? CRD_SUM : (OP == OP_MAX ? CRD_MAX : CRD_MIN);
     if (c->allreduce(&v, 1, op, c->allreduce_user) != 0) { set_error("%s: allreduce hook failed", name); return NAN; }
   }
@@ -284,8 +285,9 @@ double reduce_sqw(crd_ctx *c, const double *x, const double *w, const double *z,
   if (n > 0) {
     unsigned int blocks = grid_for((n + 1) / 2, c->sms);
     if (blocks > (unsigned)kRedBlocks) blocks = kRedBlocks;
-    red_sqw_kernel<HAS_Z><<<blocks, kRedThreads, 0, c->stream>>>(x, w, z, n, c->red_partial, c->red_ticket, c->red_result_dev);
+    red_sqw_kernel<HAS_Z><<<blocks, kRedThreads, 0, c->stream>>>(x, w, z, n, c->red_partial, c->red_ticket, red_target(c));
     if (check_launch(c, name)) return NAN;
+    if (launch_comm_exchange(c, COMM_SUM_DD, 3)) return NAN;
     if (sync_stream(c, name)) return NAN;
     hi = c->red_result_host[0]; lo = c->red_result_host[2];
   }
@@ -329,12 +331,13 @@ double flag_op(crd_ctx *c, F f, const double *x, const double *y, double *z, lon
   if (n > 0) {
     unsigned int blocks = grid_for(n);
     if (blocks > (unsigned)kRedBlocks) blocks = kRedBlocks;
-    flag_kernel<F><<<blocks, kRedThreads, 0, c->stream>>>(f, x, y, z, n, c->red_partial, c->red_ticket, c->red_result_dev);
+    flag_kernel<F><<<blocks, kRedThreads, 0, c->stream>>>(f, x, y, z, n, c->red_partial, c->red_ticket, red_target(c));
     if (check_launch(c, name)) return NAN;
+    if (launch_comm_exchange(c, COMM_MIN, 1)) return NAN;
     if (sync_stream(c, name)) return NAN;
     v = c->red_result_host[0];
   }
-  if (c->nranks > 1 && c->allreduce(&v, 1, CRD_MIN, c->allreduce_user) != 0) { set_error("%s: allreduce hook failed", name); return NAN; }
+  if (c->nranks > 1 && !c->dev_comm && c->allreduce(&v, 1, CRD_MIN, c->allreduce_user) != 0) { set_error("%s: allreduce hook failed", name); return NAN; }
   return v;
 }
 
@@ -605,18 +608,19 @@ static int erk_finish_impl(bool seq, int s, const realtype *hb, const realtype *
     if (blocks > (unsigned)kRedBlocks) blocks = kRedBlocks;
 #define CRD_FIN_CASE(S_)                                                                                                     \
   case S_:                                                                                                                   \
-    if (seq) erk_finish_kernel<S_, true><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev); \
-    else erk_finish_kernel<S_, false><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev);    \
+    if (seq) erk_finish_kernel<S_, true><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, red_target(c)); \
+    else erk_finish_kernel<S_, false><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, red_target(c));    \
     break;
     switch (s) {
       CRD_FIN_CASE(1) CRD_FIN_CASE(2) CRD_FIN_CASE(3) CRD_FIN_CASE(4) CRD_FIN_CASE(5) CRD_FIN_CASE(6) CRD_FIN_CASE(7)
       default:
-        if (seq) erk_finish_kernel<8, true><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev);
-        else erk_finish_kernel<8, false><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, c->red_result_dev);
+        if (seq) erk_finish_kernel<8, true><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, red_target(c));
+        else erk_finish_kernel<8, false><<<blocks, kRedThreads, 0, c->stream>>>(a, len, c->red_partial, c->red_ticket, red_target(c));
         break;
     }
 #undef CRD_FIN_CASE
     if (check_launch(c, "erk_finish_kernel")) return -1;
+    if (launch_comm_exchange(c, COMM_SUM_DD, 3)) return -1;
     if (sync_stream(c, "N_VErkFinish_Crd")) return -1;
     hi = c->red_result_host[0]; y2 = c->red_result_host[1]; lo = c->red_result_host[2];
   }

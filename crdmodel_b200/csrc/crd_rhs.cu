@@ -50,9 +50,7 @@ crd_grid *crd_grid_create(crd_ctx *ctx, const crd_params *p) {
   // ghost block + push ticket
   HaloLayout L{g->nx};
   if ((e = cudaMalloc(&g->halo_local, L.bytes())) != cudaSuccess ||
-      (e = cudaMemset(g->halo_local, 0, L.bytes())) != cudaSuccess ||
-      (e = cudaMalloc(&g->push_ticket, sizeof(unsigned long long))) != cudaSuccess ||
-      (e = cudaMemset(g->push_ticket, 0, sizeof(unsigned long long))) != cudaSuccess) {
+      (e = cudaMemset(g->halo_local, 0, L.bytes())) != cudaSuccess) {
     set_error("crd_grid_create: %s", cudaGetErrorString(e));
     crd_grid_destroy(g);
     return nullptr;
@@ -66,7 +64,7 @@ void crd_grid_destroy(crd_grid *g) {
   cudaStreamSynchronize(g->ctx->stream);
   if (g->prev_ipc && g->halo_prev) cudaIpcCloseMemHandle(g->halo_prev);
   if (g->next_ipc && g->halo_next && g->halo_next != g->halo_prev) cudaIpcCloseMemHandle(g->halo_next);
-  cudaFree(g->cth); cudaFree(g->brow); cudaFree(g->halo_local); cudaFree(g->push_ticket);
+  cudaFree(g->cth); cudaFree(g->brow); cudaFree(g->halo_local);
   if (g->fin_partial) cudaFree(g->fin_partial);
   if (g->res_bar) cudaFree(g->res_bar);
   if (g->res_partial) cudaFree(g->res_partial);
@@ -74,7 +72,6 @@ void crd_grid_destroy(crd_grid *g) {
   if (g->stage_y) cudaFree(g->stage_y);
   if (g->stage_ydot) cudaFree(g->stage_ydot);
   if (g->s_in) cudaStreamDestroy(g->s_in);
-  if (g->s_aux) { cudaStreamSynchronize(g->s_aux); cudaStreamDestroy(g->s_aux); cudaEventDestroy(g->ev_y); cudaEventDestroy(g->ev_b); }
   if (g->s_out) cudaStreamDestroy(g->s_out);
   for (int i = 0; i < g->n_chunks; ++i) { cudaEventDestroy(g->ev_in[i]); cudaEventDestroy(g->ev_k[i]); }
   delete[] g->ev_in; delete[] g->ev_k;
@@ -137,54 +134,64 @@ int crd_grid_halo_connect_local(crd_grid *g, crd_grid *prev, crd_grid *next) {
   return 0;
 }
 
-static int launch_push(crd_grid *g, const StateRef &S, cudaStream_t st) {
-  g->epoch++;
+// ---- halo exchange of a phi-split grid (what Exchange() does with MPI_Isend / Irecv / Wait, FHNmodel_torus.cpp:775-950) ----
+// Every evaluation has an epoch; the ghost rows are double-buffered by its parity (a rank can be at most one evaluation ahead
+// of a neighbour: it needs the neighbour's rows of epoch e to finish e).  Two ways to run one:
+//   in the launch   (default; tiled and streaming kernels) ONE launch per evaluation: its first CTAs push this slab's boundary
+//                   rows into the neighbours' ghost rows and publish them strip by strip, the tiles / row segments that touch
+//                   a ghost row are scheduled last and acquire their strip's flag — the exchange overlaps the interior rows;
+//   as launches     (direct kernel of the small meshes, crd_grid_set_overlap(g, 0), crd_rhs_post_halo): push kernel, wait
+//                   kernel, evaluation.
+static HaloSync halo_sync(crd_grid *g, bool push, bool wait) {
   HaloLayout L{g->nx};
   const int par = (int)(g->epoch & 1ULL);
+  HaloSync h;
+  if (push) {
+    h.push_prev = (double *)(g->halo_prev + L.ghost_off(par, 1));      // my row js is the row above prev's je
+    h.push_next = (double *)(g->halo_next + L.ghost_off(par, 0));      // my row je is the row below next's js
+    h.flag_prev = (unsigned long long *)(g->halo_prev + L.flag_off(1));
+    h.flag_next = (unsigned long long *)(g->halo_next + L.flag_off(0));
+  }
+  if (wait) {
+    h.wait_south = (const unsigned long long *)(g->halo_local + L.flag_off(0));
+    h.wait_north = (const unsigned long long *)(g->halo_local + L.flag_off(1));
+  }
+  h.epoch = g->epoch;
+  h.timeout_ns = g->ctx->halo_timeout_ns;
+  h.err = g->ctx->err_dev;
+  return h;
+}
+
+static int launch_push(crd_grid *g, const StateRef &S, cudaStream_t st) {
+  g->epoch++;
   RhsArgs a = make_args(g, 0.0, S, nullptr, 0, g->nyl, slab_row(0), slab_row(0));
-  double *pn = (double *)(g->halo_prev + L.ghost_off(par, 1)), *ns = (double *)(g->halo_next + L.ghost_off(par, 0));
-  unsigned long long *pf = (unsigned long long *)(g->halo_prev + L.flag_off(1)), *nf = (unsigned long long *)(g->halo_next + L.flag_off(0));
-  if (S.n > 0 && g->p.arith == CRD_ARITH_EXACT) halo_push_kernel<true, true><<<kPushBlocks, 256, 0, st>>>(a, pn, ns, pf, nf, g->push_ticket, g->epoch);
-  else if (S.n > 0) halo_push_kernel<true, false><<<kPushBlocks, 256, 0, st>>>(a, pn, ns, pf, nf, g->push_ticket, g->epoch);
-  else halo_push_kernel<false, false><<<kPushBlocks, 256, 0, st>>>(a, pn, ns, pf, nf, g->push_ticket, g->epoch);
+  a.hs = halo_sync(g, true, false);
+  const unsigned nb = (unsigned)HaloLayout{g->nx}.nstrips();
+  if (S.n > 0 && g->p.arith == CRD_ARITH_EXACT) halo_push_kernel<true, true><<<nb, 256, 0, st>>>(a);
+  else if (S.n > 0) halo_push_kernel<true, false><<<nb, 256, 0, st>>>(a);
+  else halo_push_kernel<false, false><<<nb, 256, 0, st>>>(a);
   return check_launch(g->ctx, "halo_push_kernel");
 }
 
 static int launch_wait(crd_grid *g, cudaStream_t st) {
-  HaloLayout L{g->nx};
-  halo_wait_kernel<<<1, 2, 0, st>>>((const unsigned long long *)(g->halo_local + L.flag_off(0)),
-                                    (const unsigned long long *)(g->halo_local + L.flag_off(1)), g->epoch, g->ctx->err_dev);
+  RhsArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.nx = g->nx;
+  a.hs = halo_sync(g, false, true);
+  halo_wait_kernel<<<1, 256, 0, st>>>(a);
   return check_launch(g->ctx, "halo_wait_kernel");
 }
 
-// Ring evaluation, overlapped: the boundary rows travel on the grid's auxiliary stream while the interior rows
-// (which need no neighbour data) are computed on the main stream.
-//   main: --ev_y--> [ interior rows B .. nyl-B ] ------------------------- wait ev_b --> (caller's next work)
-//   aux : wait ev_y, [push rows 0 / nyl-1 to the neighbours], [wait for theirs], [rows 0..B), [rows nyl-B..nyl), ev_b
-// B = kEdgeRows (a whole number of tile rows).  Slabs too thin to split run everything on the main stream.
-constexpr long long kEdgeRows = 32;
-
-static int ensure_aux(crd_grid *g) {
-  if (g->s_aux) return 0;
-  // highest priority: the few CTAs of push / wait / edge bands must be scheduled as soon as slots free up,
-  // not after the 65k interior CTAs of the main stream have all been dispatched
-  int prio_lo = 0, prio_hi = 0;
-  CRD_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  CRD_CUDA(cudaStreamCreateWithPriority(&g->s_aux, cudaStreamNonBlocking, prio_hi));
-  CRD_CUDA(cudaEventCreateWithFlags(&g->ev_y, cudaEventDisableTiming));
-  CRD_CUDA(cudaEventCreateWithFlags(&g->ev_b, cudaEventDisableTiming));
-  return 0;
+// does the kernel that will evaluate this state carry the exchange inside its launch?
+static bool exchange_in_launch(const crd_grid *g, int nlc, bool finish) {
+  if (!g->overlap) return false;
+  return finish || kernel_has_halo(resolved_variant(g, g->nx, g->nyl, nlc));
 }
 
 static int post_state(crd_grid *g, const StateRef &S) {
   if (!g->connected) return 0;  // single rank: the slab wraps onto itself
   if (g->epoch != g->computed) { set_error("crd_rhs_post_halo: previous epoch was posted but never computed"); return -1; }
-  g->split = g->overlap && g->nyl >= 4 * kEdgeRows;
-  if (!g->split) return launch_push(g, S, g->ctx->stream);
-  if (ensure_aux(g)) return -1;
-  CRD_CUDA(cudaEventRecord(g->ev_y, g->ctx->stream));      // the state is complete at this point of the main stream
-  CRD_CUDA(cudaStreamWaitEvent(g->s_aux, g->ev_y, 0));
-  return launch_push(g, S, g->s_aux);
+  return launch_push(g, S, g->ctx->stream);
 }
 
 // Last stage fused with the step finish: every launch of the evaluation writes its per-CTA sums into its own region.
@@ -205,36 +212,35 @@ static int launch_part(crd_grid *g, const RhsArgs &a, cudaStream_t st, FinCtx *f
   return 0;
 }
 
-static int compute_state(crd_grid *g, double t, const StateRef &S, double *ydot, FinCtx *fc = nullptr) {
+// posted: the boundary rows of this evaluation were pushed by a launch of their own (crd_rhs_post_halo) — otherwise, on a
+// connected grid, this call starts the epoch itself
+static int compute_state(crd_grid *g, double t, const StateRef &S, double *ydot, bool posted, FinCtx *fc = nullptr) {
   cudaStream_t st = g->ctx->stream;
-  const long long nyl = g->nyl, B = kEdgeRows;
+  const long long nyl = g->nyl;
   if (!g->connected) {
     RhsArgs a = make_args(g, t, S, ydot, 0, nyl, slab_row(nyl - 1), slab_row(0));
     if (launch_part(g, a, st, fc)) return -1;
     g->rhs_count++;
     return 0;
   }
-  if (g->epoch == g->computed) { set_error("crd_rhs_compute: no halo posted for this evaluation"); return -1; }
+  const bool fused = exchange_in_launch(g, S.n, fc != nullptr);
+  if (posted) {
+    if (g->epoch == g->computed) { set_error("crd_rhs_compute: no halo posted for this evaluation"); return -1; }
+  } else {
+    if (g->epoch != g->computed) { set_error("crd_rhs: previous epoch was posted but never computed"); return -1; }
+    if (fused) g->epoch++;                              // the launch below pushes
+    else if (launch_push(g, S, st)) return -1;
+  }
   HaloLayout L{g->nx};
   const int par = (int)(g->epoch & 1ULL);
   const double *gs = (const double *)(g->halo_local + L.ghost_off(par, 0));
   const double *gn = (const double *)(g->halo_local + L.ghost_off(par, 1));
-  if (!g->split) {
-    if (launch_wait(g, st)) return -1;
-    RhsArgs a = make_args(g, t, S, ydot, 0, nyl, ext_row(gs), ext_row(gn));
-    if (launch_part(g, a, st, fc)) return -1;
-  } else {
-    // interior rows on the main stream: their neighbours are rows of this slab
-    RhsArgs ai = make_args(g, t, S, ydot, B, nyl - B, slab_row(B - 1), slab_row(nyl - B));
-    if (launch_part(g, ai, st, fc)) return -1;
-    // edge rows on the auxiliary stream, once the neighbours' rows of this epoch have landed
-    if (launch_wait(g, g->s_aux)) return -1;
-    RhsArgs as = make_args(g, t, S, ydot, 0, B, ext_row(gs), slab_row(B));
-    RhsArgs an = make_args(g, t, S, ydot, nyl - B, nyl, slab_row(nyl - B - 1), ext_row(gn));
-    if (launch_part(g, as, g->s_aux, fc) || launch_part(g, an, g->s_aux, fc)) return -1;
-    CRD_CUDA(cudaEventRecord(g->ev_b, g->s_aux));
-    CRD_CUDA(cudaStreamWaitEvent(st, g->ev_b, 0));
-  }
+  RhsArgs a = make_args(g, t, S, ydot, 0, nyl, ext_row(gs), ext_row(gn));
+  if (fused) {
+    a.hs = halo_sync(g, !posted, true);
+    a.hs.edge_last = 1;
+  } else if (launch_wait(g, st)) return -1;
+  if (launch_part(g, a, st, fc)) return -1;
   g->computed = g->epoch;
   g->rhs_count++;
   return 0;
@@ -251,12 +257,13 @@ int crd_rhs_post_halo(crd_grid *g, const double *y) {
 int crd_rhs_compute(crd_grid *g, double t, const double *y, double *ydot) {
   if (!g || !y || !ydot) { set_error("crd_rhs_compute: null argument"); return -1; }
   if (use(g->ctx)) return -1;
-  return compute_state(g, t, plain_state(y), ydot);
+  return compute_state(g, t, plain_state(y), ydot, true);
 }
 
 int crd_rhs(crd_grid *g, double t, const double *y, double *ydot) {
-  if (crd_rhs_post_halo(g, y)) return -1;
-  return crd_rhs_compute(g, t, y, ydot);
+  if (!g || !y || !ydot) { set_error("crd_rhs: null argument"); return -1; }
+  if (use(g->ctx)) return -1;
+  return compute_state(g, t, plain_state(y), ydot, false);
 }
 
 // ydot = f(t, sum_j c[j]*X[j]) without materialising the combination (explicit RK stage assembly fused into the
@@ -270,8 +277,7 @@ int crd_rhs_lincomb(crd_grid *g, double t, int n, const double *c, const double 
     if (!X_dev[j] || X_dev[j] == ydot) { set_error("crd_rhs_lincomb: null or aliased vector"); return -1; }
     S.x[j] = X_dev[j]; S.c[j] = c[j];
   }
-  if (post_state(g, S)) return -1;
-  return compute_state(g, t, S, ydot);
+  return compute_state(g, t, S, ydot, false);
 }
 
 int crd_f_lincomb(realtype t, int n, const realtype *c, N_Vector *X, N_Vector ydot, void *user_data) {
@@ -287,9 +293,10 @@ int crd_f_lincomb(realtype t, int n, const realtype *c, N_Vector *X, N_Vector yd
 
 // The last stage of an s-stage explicit RK step fused with the step finish: with X = (yn, F_0 .. F_{s-2}) and
 // F_{s-1} = f(t, sum_j c[j] X[j]) (never stored),  ynew = yn + sum_j hb[j] F_j,  err = sum_j hd[j] F_j,
-// out[0] = sum (err_i w_i)^2, out[1] = sum (ynew_i w'_i)^2 as N_VErkFinish_Crd defines them.  ynew has the bits of
-// crd_rhs_lincomb followed by N_VErkFinish_Crd.  Returns 1 when it does not apply (not 5 stages, a phi-split grid, a mesh
-// too small to stream): the caller then issues the two separate operations.
+// out[0] = sum (err_i w_i)^2, out[1] = sum (ynew_i w'_i)^2 as N_VErkFinish_Crd defines them (global sums on a phi-split grid,
+// whose halo exchange rides inside the same launch).  ynew has the bits of crd_rhs_lincomb followed by N_VErkFinish_Crd /
+// N_VErkFinishSeq_Crd (FAST / EXACT grid).  Returns 1 when it does not apply (not 5 stages, a mesh too small to stream) — decided
+// before anything is sent to the neighbours: the caller then issues the two separate operations.
 int crd_rhs_lincomb_finish(crd_grid *g, double t, int s, const double *c, const double *hb, const double *hd,
                            const double *const *X_dev, double *ynew_dev, double rtol, double atol, double out[2]) {
   if (!g || !c || !hb || !hd || !X_dev || !ynew_dev || !out) { set_error("crd_rhs_lincomb_finish: null argument"); return -1; }
@@ -307,10 +314,13 @@ int crd_rhs_lincomb_finish(crd_grid *g, double t, int s, const double *c, const 
   FinCtx fc;
   for (int j = 0; j < kMaxLc; ++j) { fc.fin.hb[j] = hb[j]; fc.fin.hd[j] = hd[j]; }
   fc.fin.rtol = rtol; fc.fin.atol = atol; fc.fin.partial = g->fin_partial;
-  if (post_state(g, S)) return -1;
-  if (compute_state(g, t, S, ynew_dev, &fc)) return -1;
-  // every launch has been joined into the main stream: add the regions in a fixed order
-  fin_reduce_kernel<<<1, 256, 0, ctx->stream>>>(g->fin_partial, fc.nregions, fc.nblocks[0], fc.nblocks[1], fc.nblocks[2], ctx->red_result_dev);
+  if (compute_state(g, t, S, ynew_dev, false, &fc)) return -1;
+  // add the per-CTA sums in a fixed order
+  // ... and, with the device-side allreduce wired, exchange them with the other ranks in the same launch
+  const CommTab *tab = ctx->dev_comm ? ctx->comm_tab : nullptr;
+  if (tab) ++ctx->comm_seq;
+  fin_reduce_kernel<<<1, 256, 0, ctx->stream>>>(g->fin_partial, fc.nregions, fc.nblocks[0], fc.nblocks[1], fc.nblocks[2], ctx->red_result_dev,
+                                                tab, ctx->comm_seq);
   if (check_launch(ctx, "fin_reduce_kernel")) return -1;
   if (sync_stream(ctx, "crd_rhs_lincomb_finish")) return -1;
   double hi = ctx->red_result_host[0], y2 = ctx->red_result_host[1], lo = ctx->red_result_host[2];

@@ -113,6 +113,59 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
+// ---- halo exchange inside a launch (crd_grid.cuh: HaloSync) ------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// one thread: until the strip's flag has reached this evaluation's epoch (acquire, system scope: the rows were stored by
+// another GPU) or the timeout has passed — then the error word is raised and the launch goes on with stale rows; the host
+// sees the word at its next wait for the stream and fails the context (crd_common.cuh: device_failed)
+__device__ __noinline__ void halo_acquire(const unsigned long long *flag, unsigned long long epoch, long long timeout_ns, int *err, int code) {
+  unsigned long long t0 = 0;
+  for (unsigned spin = 0;; ++spin) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= epoch) break;
+    if ((spin & 15u) == 15u) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if ((long long)(now - t0) > timeout_ns) { *err = code; __threadfence_system(); break; }
+      __nanosleep(200);
+    }
+  }
+  // rows fetched next by the async proxy (TMA bulk copies) must be ordered after the acquire as well
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+// 256 threads: strip `strip` of this slab's first row -> prev's north ghost row, of its last row -> next's south ghost row
+template <bool LC, bool SEQ>
+__device__ __forceinline__ void halo_push_strip(const RhsArgs &a, long long strip, int t) {
+  const long long col = strip * kHaloStrip + t;
+  if (col < a.nx) {
+    reinterpret_cast<double2 *>(a.hs.push_prev)[col] = state2<LC, SEQ>(a, col);
+    reinterpret_cast<double2 *>(a.hs.push_next)[col] = state2<LC, SEQ>(a, (a.nyl - 1) * a.nx + col);
+  }
+  __threadfence_system();
+}
+// one thread, after a barrier over the pushing threads: the strip is complete over there
+__device__ __forceinline__ void halo_publish(const RhsArgs &a, long long strip) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.hs.flag_prev + strip), "l"(a.hs.epoch) : "memory");
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.hs.flag_next + strip), "l"(a.hs.epoch) : "memory");
+}
+// work that touches a ghost row goes last (edge_last): index b of n_outer x n_inner items -> (outer, inner), the first and the
+// last outer index after all the others
+__device__ __forceinline__ void edge_last_coords(long long b, long long n_outer, long long n_inner, int edge_last, long long &outer, long long &inner) {
+  if (edge_last && n_outer >= 3) {
+    const long long mid = (n_outer - 2) * n_inner;
+    if (b < mid) { outer = 1 + b / n_inner; inner = b - (outer - 1) * n_inner; }
+    else { const long long e = b - mid; outer = (e < n_inner) ? 0 : n_outer - 1; inner = (e < n_inner) ? e : e - n_inner; }
+  } else {
+    outer = b / n_inner; inner = b - outer * n_inner;
+  }
+}
+
 template <int MODEL, bool EXACT, int TX, int TY, int MINB, bool ACC, bool LC, int NG>
 __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
   constexpr int PITCH = TX + 2;            // points per staged row (west halo + TX + east halo)
@@ -127,12 +180,33 @@ __global__ void __launch_bounds__(256, MINB) rhs_tile_kernel(const RhsArgs a) {
 
   const long long nx = a.nx, nyl = a.nyl;
   const long long tiles_x = (nx + TX - 1) / TX;
-  const long long ty = blockIdx.x / tiles_x;
-  const long long tx = blockIdx.x - ty * tiles_x;
+  long long ty, tx;
+  edge_last_coords(blockIdx.x, (nyl + TY - 1) / TY, tiles_x, a.hs.edge_last, ty, tx);
   const long long i0 = tx * TX, j0 = ty * TY;
   const int w = (nx - i0 < TX) ? (int)(nx - i0) : TX;            // valid columns of this tile
   const int h = (nyl - j0 < TY) ? (int)(nyl - j0) : TY;          // valid rows of this tile
   const unsigned bar = smem_u32(mbar);
+
+  // phi-split grid, exchange inside this launch: the first CTAs push the slab's boundary rows to the neighbours before
+  // anything else (so a CTA never waits before it has pushed); a tile that touches a ghost row acquires that strip's flag
+  if (a.hs.push_prev) {
+    const long long nstrips = (nx + kHaloStrip - 1) / kHaloStrip;
+    for (long long sp = blockIdx.x; sp < nstrips; sp += gridDim.x) {
+      halo_push_strip<LC, EXACT>(a, sp, threadIdx.x);
+      __syncthreads();
+      if (threadIdx.x == 0) halo_publish(a, sp);
+    }
+  }
+  {
+    const bool need_s = a.hs.wait_south != nullptr && j0 == 0, need_n = a.hs.wait_north != nullptr && j0 + h == nyl;
+    if (need_s || need_n) {
+      if (threadIdx.x == 0) {
+        if (need_s) halo_acquire(a.hs.wait_south + i0 / kHaloStrip, a.hs.epoch, a.hs.timeout_ns, a.hs.err, 100);
+        if (need_n) halo_acquire(a.hs.wait_north + i0 / kHaloStrip, a.hs.epoch, a.hs.timeout_ns, a.hs.err, 101);
+      }
+      __syncthreads();
+    }
+  }
 
   if (!LC) {
   if (threadIdx.x == 0) {
@@ -374,7 +448,8 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
     if (lane != 0) return;
     long long it = 0;   // stage counter
     for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-      const long long strip = u % strips, seg = u / strips;
+      long long strip, seg;
+      edge_last_coords(u, segs, strips, a.hs.edge_last, seg, strip);
       const long long i0 = strip * TX, jA = seg * seg_rows, jB = (jA + seg_rows < nyl) ? jA + seg_rows : nyl;
       const int w = (nx - i0 < TX) ? (int)(nx - i0) : TX;
       const bool west_in = i0 > 0, east_in = i0 + w < nx;
@@ -394,6 +469,10 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
         for (int rr = 0; rr < nr; ++rr) {
           const long long jr = j0 + rr;
           const bool ext = (jr < 0 && a.south) || (jr >= nyl && a.north);   // an already combined ghost row
+          if (ext) {   // exchange inside this launch: the neighbour's strip of that row must have landed
+            if (jr < 0 && a.hs.wait_south) halo_acquire(a.hs.wait_south + strip, a.hs.epoch, a.hs.timeout_ns, a.hs.err, 102);
+            if (jr >= nyl && a.hs.wait_north) halo_acquire(a.hs.wait_north + strip, a.hs.epoch, a.hs.timeout_ns, a.hs.err, 103);
+          }
           const int nvec = (PLAIN || ext) ? 1 : NV;
           for (int v = 0; v < nvec; ++v) {
             const double2 *row;
@@ -430,8 +509,20 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
   for (int j = 0; j < NV; ++j) lcc[j] = a.lc_c[j];
   const bool edge_lane = (lane == 0) || (lane == 31);
   const int edge_q = (lane == 0) ? c : c + 2;   // slot index of the neighbour column that lives in another warp
+  // phi-split grid, exchange inside this launch: before anything else the consumers of the first CTAs push the slab's
+  // boundary rows (of the stage state when this is a fused stage) to the neighbours
+  if (a.hs.push_prev) {
+    const long long nstrips = (nx + kHaloStrip - 1) / kHaloStrip;
+    for (long long sp = blockIdx.x; sp < nstrips; sp += gridDim.x) {
+      halo_push_strip<!PLAIN, EXACT>(a, sp, c);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (c == 0) halo_publish(a, sp);
+    }
+  }
   for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-    const int strip = (int)(u % strips), seg = (int)(u / strips);
+    long long strip_l, seg_l;
+    edge_last_coords(u, segs, strips, a.hs.edge_last, seg_l, strip_l);
+    const int strip = (int)strip_l, seg = (int)seg_l;
     const int i0 = strip * TX, jA = seg * seg_rows, jB = (jA + seg_rows < nyli) ? jA + seg_rows : nyli;
     const int w = (nxi - i0 < TX) ? (nxi - i0) : TX;
     const bool active = c < w;
@@ -578,8 +669,11 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
 
 // adds the per-CTA sums of a FIN stage (up to three launches, one region of [3][kRedBlocks] each) in a fixed order, the error
 // sum in double-double; result[0] = hi, result[1] = sum (ynew w')^2, result[2] = lo go to mapped pinned host memory
-__global__ void __launch_bounds__(256) fin_reduce_kernel(const double *partial, int nregions, int n0, int n1, int n2, double *result) {
+// on a phi-split grid with the device-side allreduce wired (T != nullptr) the ranks' sums are exchanged here as well
+__global__ void __launch_bounds__(256) fin_reduce_kernel(const double *partial, int nregions, int n0, int n1, int n2, double *result,
+                                                         const CommTab *T, unsigned long long seq) {
   __shared__ double sm[3][8];
+  __shared__ double gv[kCommVals];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double sh = 0.0, sl = 0.0, sy = 0.0;
   for (int r = 0; r < nregions; ++r) {
@@ -594,7 +688,12 @@ __global__ void __launch_bounds__(256) fin_reduce_kernel(const double *partial, 
   if (threadIdx.x == 0) {
     sh = sm[0][0]; sy = sm[1][0]; sl = sm[2][0];
     for (int w = 1; w < 8; ++w) { dd_merge(sh, sl, sm[0][w], sm[2][w]); sy += sm[1][w]; }
-    result[0] = sh; result[1] = sy; result[2] = sl;
+    gv[0] = sh; gv[1] = sy; gv[2] = sl; gv[3] = 0.0;
+  }
+  __syncthreads();
+  if (T) comm_allreduce_block(T, seq, COMM_SUM_DD, kCommVals, gv);
+  if (threadIdx.x == 0) {
+    result[0] = gv[0]; result[1] = gv[1]; result[2] = gv[2];
     __threadfence_system();
   }
 }
@@ -663,37 +762,46 @@ int launch_stage_finish(crd_grid *g, const RhsArgs &a, const StageFin &fin, cuda
   return 1;
 }
 
+// Which kernel evaluates a launch of nx x nyl points with nlc input vectors (0 = a plain state) on this grid:
+//   1..5 the direct kernel (rows per thread, min CTAs/SM): 1 (2,4) | 2 (8,2) | 3 (1,4) | 4 (4,3) | 5 (4,4)
+//   10, 13, 15 the tiled kernel (TX, TY, min CTAs/SM): 10 (128,16,4) | 13 (256,16,3) | 15 = 13 with flag-and-redo instead of a
+//              branch per point;   20, 21 the streaming kernel with 2 | 3 CTAs per SM.
+// Grid variant 0 = automatic.  Large slabs (>= 4 Mi points, HBM-bound): the TMA-tiled kernel wherever a tile row is reasonably
+// full; the streaming kernel for the fused stages (its once-per-row fetch beats the tiled kernel's register-staged tiles: 3
+// CTAs/SM for 2 or 3 input vectors, 2 for 5).  Small slabs (the reference's default 400 x 1600 / 100 x 400 grids live in L2 and
+// are bound by launch latency and by how many CTAs a partial wave gets): the direct kernel with 2 rows per thread.  Measured:
+// profiles/README.md.  Tilings that measured slower (11, 12, 14, 16-18; 23 / 24 for the fused finish) are compiled only with
+// -DCRD_PROFILING_VARIANTS.  The tiled and the streaming kernels carry the halo exchange inside the launch (kernel_has_halo).
+inline int resolved_variant(const crd_grid *g, long long nx, long long nyl, int nlc) {
+  const bool exact = g->p.arith == CRD_ARITH_EXACT;
+  int variant = g->variant;
+  const bool big = nx * nyl >= (4LL << 20);
+  if (variant == 0) {
+    if (!big) variant = 1;
+    else variant = (nx >= 192) ? ((exact && !is_fhn(g->p.model)) ? 15 : 13) : (nx >= 96) ? 10 : 5;
+    if (nlc == 5 && nx >= 192 && big) variant = 20;
+    if ((nlc == 2 || nlc == 3) && nx >= 192 && big) variant = 21;
+  }
+#ifndef CRD_PROFILING_VARIANTS
+  if (variant >= 10 && variant != 10 && variant != 13 && variant != 15 && variant != 20 && variant != 21) variant = 13;   // not in this build
+#endif
+  if (variant < 1) variant = 1;
+  const bool stream_ok = nlc == 0 || nlc == 2 || nlc == 3 || nlc == 5;
+  if (variant == 21 && !(nlc == 0 || nlc == 2 || nlc == 3)) variant = 20;
+  if (variant == 20 && !stream_ok) variant = 13;
+  return variant;
+}
+inline bool kernel_has_halo(int variant) { return variant >= 10; }
+
 template <int MODEL, bool EXACT>
 int launch_model(crd_grid *g, const RhsArgs &a_in, cudaStream_t st) {
-  // variant 0 = automatic.  Large slabs (>= 4 Mi points, HBM-bound): the TMA-tiled kernel wherever a tile row is
-  // reasonably full.  Small slabs (the reference's default 400x1600 / 100x400 grids live in L2 and are bound by
-  // launch latency and by how many CTAs a partial wave gets): the direct kernel with 2 rows per thread.
-  // explicit: direct kernel (rows per thread, min CTAs/SM) 1 (2,4) | 2 (8,2) | 3 (1,4) | 4 (4,3) | 5 (4,4)
-  //           tiled kernel (TX, TY, min CTAs/SM) 10 (128,16,4) | 13 (256,16,3) | 15 = 13 with flag-and-redo instead of a
-  //           branch per point; streaming kernel 20 (2 CTAs/SM) | 21 (3 CTAs/SM).  Tilings that measured slower (11, 12, 14,
-  //           16-18; 23 / 24 for the fused finish) are compiled only with -DCRD_PROFILING_VARIANTS.
-  int variant = g->variant;
-  if (variant == 0) {
-    const long long pts = a_in.nx * a_in.nyl;
-    if (pts < (4LL << 20)) variant = 1;
-    else variant = (a_in.nx >= 192) ? ((EXACT && !is_fhn(MODEL)) ? 15 : 13) : (a_in.nx >= 96) ? 10 : 5;   // measured: profiles/README.md
-  }
-  // measured (profiles/README.md): the streaming kernel wins only for the widest fused stage (5 input vectors,
-  // where its once-per-row fetch beats the tiled kernel's register-staged tiles); the tiled kernel everywhere else
-  if (g->variant == 0 && a_in.nlc == 5 && a_in.nx >= 192 && a_in.nx * a_in.nyl >= (4LL << 20)) variant = 20;
-  // 2 or 3 input vectors: the streaming kernel with 3 CTAs per SM (24 consumer warps) is 1-3 % / 13-15 % ahead of the staged tile
-  if (g->variant == 0 && (a_in.nlc == 2 || a_in.nlc == 3) && a_in.nx >= 192 && a_in.nx * a_in.nyl >= (4LL << 20)) variant = 21;
+  const int variant = resolved_variant(g, a_in.nx, a_in.nyl, a_in.nlc);
   if (variant == 21) {   // streaming kernel with 3 CTAs per SM (plain state, 2 or 3 input vectors)
     if (a_in.nlc == 2) return launch_stream_nv<MODEL, EXACT, 2, false, false, 3>(g, a_in, st);
     if (a_in.nlc == 3) return launch_stream_nv<MODEL, EXACT, 3, false, false, 3>(g, a_in, st);
-    if (a_in.nlc == 0) return launch_stream_nv<MODEL, EXACT, 1, true, false, 3>(g, a_in, st);
-    variant = 20;
+    return launch_stream_nv<MODEL, EXACT, 1, true, false, 3>(g, a_in, st);
   }
-  if (variant == 20) {   // streaming kernel (persistent CTAs, shared-memory row ring)
-    const int r = launch_stream<MODEL, EXACT>(g, a_in, st);
-    if (r <= 0) return r;
-    variant = 13;
-  }
+  if (variant == 20) return launch_stream<MODEL, EXACT>(g, a_in, st);   // streaming kernel (persistent CTAs, shared-memory row ring)
   switch (variant) {
     case 10: return launch_tile<MODEL, EXACT, 128, 16, 4, false>(g, a_in, st);
     case 13: return launch_tile<MODEL, EXACT, 256, 16, 3, false>(g, a_in, st);
@@ -792,48 +900,24 @@ RhsArgs make_args(const crd_grid *g, double t, const StateRef &S, double *ydot, 
   return a;
 }
 
-// ---- halo ring: push first/last row into the neighbours' ghost blocks, flag the epoch ------------------
+// ---- halo exchange as launches of its own (kernels without the in-launch exchange; crd_rhs_post_halo) ------------------
 template <bool LC, bool SEQ>
-__global__ void __launch_bounds__(256) halo_push_kernel(const RhsArgs a, double *prev_north, double *next_south,
-                                                        unsigned long long *prev_flag, unsigned long long *next_flag,
-                                                        unsigned long long *ticket, unsigned long long epoch) {
-  const long long nx = a.nx, nyl = a.nyl;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  double2 *pn = reinterpret_cast<double2 *>(prev_north), *ns = reinterpret_cast<double2 *>(next_south);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nx; i += stride) {
-    pn[i] = state2<LC, SEQ>(a, i);                     // my row js is the row above prev's je
-    ns[i] = state2<LC, SEQ>(a, (nyl - 1) * nx + i);    // my row je is the row below next's js
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned long long done = atomicAdd(ticket, 1ULL) + 1ULL;
-    if (done == gridDim.x * epoch) {  // last block of this epoch (ticket is never reset)
-      __threadfence_system();
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(prev_flag), "l"(epoch) : "memory");
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(next_flag), "l"(epoch) : "memory");
-    }
+__global__ void __launch_bounds__(256) halo_push_kernel(const RhsArgs a) {
+  const long long nstrips = (a.nx + kHaloStrip - 1) / kHaloStrip;
+  for (long long sp = blockIdx.x; sp < nstrips; sp += gridDim.x) {
+    halo_push_strip<LC, SEQ>(a, sp, threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) halo_publish(a, sp);
   }
 }
 
-__global__ void halo_wait_kernel(const unsigned long long *flag_south, const unsigned long long *flag_north,
-                                 unsigned long long epoch, int *err) {
-  const unsigned long long *f = threadIdx.x == 0 ? flag_south : flag_north;
-  const long long t0 = clock64();
-  for (;;) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-    if (v >= epoch) break;
-    if (clock64() - t0 > 6000000000LL) {  // ~3 s: a neighbour never posted; report instead of hanging
-      *err = 100 + (int)threadIdx.x;
-      __threadfence_system();
-      break;
-    }
-    __nanosleep(200);
+__global__ void __launch_bounds__(256) halo_wait_kernel(const RhsArgs a) {
+  const long long nstrips = (a.nx + kHaloStrip - 1) / kHaloStrip;
+  for (long long q = threadIdx.x; q < 2 * nstrips; q += blockDim.x) {
+    const bool north = q >= nstrips;
+    halo_acquire((north ? a.hs.wait_north : a.hs.wait_south) + (north ? q - nstrips : q), a.hs.epoch, a.hs.timeout_ns, a.hs.err, north ? 105 : 104);
   }
 }
-
-constexpr int kPushBlocks = 16;
 
 // ---- initial conditions -----------------------------------------------------------------------------------
 struct IcArgs {

@@ -36,6 +36,14 @@ def ring_connect(grid, rank, world, handles):
     grid.halo_connect_ipc(handles[prev], handles[nxt])
 
 
+def comm_connect(ctx, rank, world, group=None):
+    """Wire the device-side allreduce: all-gather the contexts' mailbox handles, connect to every rank.  After this the
+    integrator's norms never leave the GPUs (no host-level allreduce hook is called)."""
+    if world == 1:
+        return
+    ctx.comm_connect_ipc(rank, world, exchange_handles(ctx.comm_handle(), group))
+
+
 def make_allreduce(group=None):
     """Host-level allreduce hook for Context.set_comm built on a (gloo) process group."""
     import torch

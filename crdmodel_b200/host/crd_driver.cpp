@@ -11,7 +11,8 @@
 // device N_Vector, fused stencil+reaction kernel, explicit RK driver through the ARKode-legacy names.
 // Ranks are GPUs: `System.gpus = G` (or CRD_GPUS=G) forks G worker processes, one per GPU, each owning a
 // phi slab; neighbours' boundary rows travel through CUDA-IPC peer mappings, norms through shared memory.
-// New optional keys (absent => the reference's behaviour): System.gpus, System.arith (exact|fast),
+// New optional keys (absent => the reference's behaviour): System.gpus, System.arith (exact|fast), System.deviceAllreduce (1),
+// System.haloTimeout (seconds),
 // System.fused (1), System.reuseFirstStage (= fused), System.resident (1), Parameters.phiMesh, Parameters.Zs / Ys,
 // System.steadyStateCommand (the reference's SolveGoldbeterODE.py protocol instead of the closed-form steady state).
 #include <pthread.h>
@@ -80,6 +81,7 @@ int check_flag(void *flagvalue, const std::string &funcname, int opt) {
 struct Shared {
   pthread_barrier_t bar;
   unsigned char handle[kMaxRanks][CRD_HALO_HANDLE_BYTES];
+  unsigned char comm[kMaxRanks][CRD_HALO_HANDLE_BYTES];
   double red[kMaxRanks][3 * kMaxRanks];
   int failed;
 };
@@ -107,7 +109,8 @@ struct Config {
   double DIFF, BETA, SURFACE_LENGTH, SURFACE_WIDTH, WAVE_LENGTH, WAVE_WIDTH, T_BOUNDARY, T_FINAL, BETA_MIN = 0, BETA_MAX = 0;
   int WAVE_INSIDE = 0, OUTPUT_TIMESTEP, NX, INCLUDE_ALL_VARS, VARY_BETA, JUST_DIFFUSION = 0, IC_TYPE = 0;
   long ny;
-  int gpus, arith, fused, reuse, resident;
+  int gpus, arith, fused, reuse, resident, dev_allreduce;
+  double halo_timeout_s = 0;
   double Zs = 0, Ys = 0;
   bool have_zs = false;
 };
@@ -158,6 +161,8 @@ Config read_config(const char *path) {
   c.arith = (ar == "fast") ? CRD_ARITH_FAST : CRD_ARITH_EXACT;
   c.fused = pt.get<int>("System.fused", 1);
   c.reuse = pt.get<int>("System.reuseFirstStage", c.fused ? 1 : 0);   // f(tn, yn) is already there from the previous step: same bits
+  c.dev_allreduce = pt.get<int>("System.deviceAllreduce", 1);
+  c.halo_timeout_s = pt.get<double>("System.haloTimeout", 0.0);   // seconds a rank waits for a neighbour's rows (0: the library's 30 s)
   c.resident = pt.get<int>("System.resident", 1);   // 1: the step loop runs as one persistent kernel when it applies
   if (!kFhn) {
     if (pt.has("Parameters.Zs") && pt.has("Parameters.Ys")) {
@@ -197,6 +202,7 @@ int run(const Config &c, int rank, int nranks) {
   if (!ctx) { cerr << "\nCUDA_ERROR: " << crd_last_error() << "\n\n"; return 1; }
   flag = crd_ctx_set_comm(ctx, rank, nranks, nranks > 1 ? shm_allreduce : NULL, NULL);
   if (check_flag(&flag, "crd_ctx_set_comm", 1)) return 1;
+  if (c.halo_timeout_s > 0) crd_ctx_set_halo_timeout(ctx, 1e3 * c.halo_timeout_s);
 
   crd_params p;
   std::memset(&p, 0, sizeof p);
@@ -212,9 +218,17 @@ int run(const Config &c, int rank, int nranks) {
   if (nranks > 1) {
     flag = crd_grid_halo_handle(grid, g_shm->handle[rank]);
     if (check_flag(&flag, "crd_grid_halo_handle", 1)) return 1;
+    flag = crd_ctx_comm_handle(ctx, g_shm->comm[rank]);
+    if (check_flag(&flag, "crd_ctx_comm_handle", 1)) return 1;
     pthread_barrier_wait(&g_shm->bar);
     flag = crd_grid_halo_connect_ipc(grid, g_shm->handle[(rank + nranks - 1) % nranks], g_shm->handle[(rank + 1) % nranks]);
     if (flag != 0) { cerr << "halo connect: " << crd_last_error() << "\n"; return 1; }
+    // the integrator's norms are finished on the devices (mailboxes over NVLink); System.deviceAllreduce = 0 keeps the
+    // shared-memory hook of crd_ctx_set_comm instead
+    if (c.dev_allreduce) {
+      flag = crd_ctx_comm_connect_ipc(ctx, rank, nranks, &g_shm->comm[0][0]);
+      if (flag != 0) { cerr << "allreduce connect: " << crd_last_error() << "\n"; return 1; }
+    }
     pthread_barrier_wait(&g_shm->bar);
   }
 
@@ -279,12 +293,13 @@ int run(const Config &c, int rank, int nranks) {
   const long N = 2 * nxl * nyl, Ntot = 2 * nx * ny;
   N_Vector y = N_VNew_Crd(ctx, N, Ntot);
   if (check_flag((void *)y, "N_VNew_Crd", 0)) { cerr << crd_last_error() << "\n"; return 1; }
-  realtype *ydata = N_VGetArrayPointer(y);     // pinned host mirror, refreshed by N_VCopyToHost_Crd
-  if (check_flag((void *)ydata, "N_VGetArrayPointer", 0)) return 1;
+  realtype *ydata = NULL;   // the reference caches N_VGetArrayPointer(y) here (:383); only the host-generated ICs need a host array
 
   if (kTorus && c.WAVE_INSIDE != 0 && c.WAVE_INSIDE != 1) printf("WaveInside must be 0 or 1");
   if (!kFhn && c.VARY_BETA == 1 && c.IC_TYPE == 2) {
     // icType 2: unseeded rand() through (float), identical on every rank (GoldbeterModel_flat.cpp:373-374)
+    ydata = N_VGetArrayPointer(y);     // pinned host mirror
+    if (check_flag((void *)ydata, "N_VGetArrayPointer", 0)) return 1;
     for (long j = 0; j < ny; ++j)
       for (long i = 0; i < nx; ++i) {
         const double a = (float)rand() / RAND_MAX * 1.4, b = (float)rand() / RAND_MAX * 1.4;
@@ -330,11 +345,22 @@ int run(const Config &c, int rank, int nranks) {
   FILE *UFID2 = fopen(outname, "w");
   if (!UFID || !UFID2) { cerr << "cannot open output files\n"; return 1; }
 
-  // output off the critical path: snapshot -> background thread formats with all host cores -> ordered write
-  crd::AsyncWriter writer(UFID, UFID2, c.INCLUDE_ALL_VARS == 1, nxl * nyl);
+  // output off the critical path (crd_writer.hpp): an output is enqueued — gather of the written variables on the device,
+  // asynchronous copy into one of three page-locked buffers — and the time loop goes on; a background thread formats
+  const bool all_vars = c.INCLUDE_ALL_VARS == 1;
+  crd_snapshot *snap = crd_snapshot_create(ctx, (int64_t)nxl * nyl, all_vars ? 2 : 1, 3);
+  if (check_flag((void *)snap, "crd_snapshot_create", 2)) { cerr << crd_last_error() << "\n"; return 1; }
+  crd::AsyncWriter writer(UFID, UFID2, all_vars, nxl * nyl);
   auto write_state = [&]() -> int {
-    if (N_VCopyToHost_Crd(y) != 0) { cerr << crd_last_error() << "\n"; return 1; }
-    writer.submit(ydata);
+    int slot;
+    while ((slot = crd_snapshot_begin(snap, N_VGetDeviceArrayPointer_Crd(y))) == -2) usleep(200);   // every buffer still being formatted
+    if (slot < 0) { cerr << crd_last_error() << "\n"; return 1; }
+    writer.submit([snap, slot]() {
+      crd::OutputView v;
+      if (crd_snapshot_wait(snap, slot, &v.v0, &v.v1) != 0) { v.v0 = nullptr; }
+      v.release = [snap, slot]() { crd_snapshot_release(snap, slot); };
+      return v;
+    });
     return 0;
   };
   if (write_state()) return 1;
@@ -353,6 +379,9 @@ int run(const Config &c, int rank, int nranks) {
       break;
     }
     if (write_state()) return 1;
+    // the ranks meet on the host before the next interval: whatever one of them spent here (a full output queue, a slow
+    // disk) cannot turn into a neighbour's halo timeout during the next evaluations
+    if (nranks > 1) pthread_barrier_wait(&g_shm->bar);
     time(&end_t);
     total_t += difftime(end_t, start_t);
     start_t = end_t;
@@ -365,6 +394,8 @@ int run(const Config &c, int rank, int nranks) {
     }
   }
   writer.finish();
+  if (writer.failed()) { cerr << "output writer: " << crd_last_error() << "\n"; flag = -1; }
+  crd_snapshot_destroy(snap);
   if (outproc) cout << "\n   ----------------------\n";
   fclose(UFID);
   fclose(UFID2);

@@ -81,6 +81,15 @@ int crd_device_count(void);
 crd_ctx *crd_ctx_create(int device, void *stream);
 void crd_ctx_destroy(crd_ctx *ctx);
 int crd_ctx_set_comm(crd_ctx *ctx, int rank, int nranks, crd_allreduce_fn fn, void *user);
+/* Device-side allreduce for the same purpose (the MPI_Allreduce inside nvector_parallel's reductions), without the host:
+ * every context exports the handle of its mailbox block, the host program gathers them (handles: nranks x
+ * CRD_HALO_HANDLE_BYTES, in rank order) and each rank connects to all.  From then on the finishing block of every reduction
+ * stores its values into all ranks' mailboxes through the NVLink peer mappings, waits for everybody's, and combines them in
+ * rank order — identical bits on every rank; the hook of crd_ctx_set_comm is no longer called.  All ranks must issue the same
+ * sequence of reductions (they do: the integrator is the same program on every rank).  *_local: contexts of one process. */
+int crd_ctx_comm_handle(crd_ctx *ctx, unsigned char handle[64]);
+int crd_ctx_comm_connect_ipc(crd_ctx *ctx, int rank, int nranks, const unsigned char *handles);
+int crd_ctx_comm_connect_local(crd_ctx *ctx, int rank, int nranks, crd_ctx *const *all);
 void *crd_ctx_stream(crd_ctx *ctx);
 int crd_ctx_device(crd_ctx *ctx);
 int crd_ctx_sync(crd_ctx *ctx);

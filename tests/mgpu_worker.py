@@ -21,6 +21,8 @@ def main():
     dist.init_process_group("gloo")
     ctx = crd.Context(local)
     ctx.set_comm(rank, world, cdist.make_allreduce())
+    if os.environ.get("CRD_TEST_HOST_ALLREDUCE") != "1":
+        cdist.comm_connect(ctx, rank, world)       # device-side allreduce (default); the host hook stays as the fallback
     ok = True
     for model in ("fhn_torus", "gb_torus", "fhn_flat"):
         nx, ny = 320, 1003

@@ -176,7 +176,10 @@ def test_phi_split_is_bitwise_invariant(crd, ctx, oracle):
     waits, so this order cannot deadlock).  Gathered ydot must equal the single-slab result bit for bit."""
     # (96, 203): thin slabs, everything on the main stream; (300, 1100): slabs tall enough for the overlapped
     # path (interior rows on the main stream, halo + edge rows on the auxiliary stream)
-    for model, nx, ny, ranks in [(m, 96, 203, (1, 2, 3, 8)) for m in MODELS] + [("fhn_torus", 300, 1100, (2, 3)), ("gb_flat", 300, 1100, (2,))]:
+    # forced variants 13 / 20 / 21: the tiled and the streaming kernels, which acquire the ghost rows' flags inside the launch
+    cases = [(m, 96, 203, (1, 2, 3, 8), None) for m in MODELS] + [("fhn_torus", 300, 1100, (2, 3), None), ("gb_flat", 300, 1100, (2,), None)]
+    cases += [("fhn_torus", 300, 1100, (2, 3), v) for v in (13, 20, 21)] + [("gb_torus", 520, 700, (2,), 15)]
+    for model, nx, ny, ranks, forced in cases:
         y = oracle.fill_state(model, 2 * nx * ny, seed=5)
         for t in (10.0, 50.0):
             one = gpu_rhs(crd, ctx, model, nx, ny, t, y, crd.ARITH_EXACT, t_boundary=38.0)
@@ -185,7 +188,7 @@ def test_phi_split_is_bitwise_invariant(crd, ctx, oracle):
                 for r in range(nr):
                     js, je = crd.decomp_phi(ny, nr, r)
                     g = crd.Grid(ctx, crd.make_params(model, nx, ny, js=js, je=je, t_boundary=38.0))
-                    g.set_variant(10 if (nr + r) % 2 else 0)      # mix the tiled and the direct kernel
+                    g.set_variant(forced if forced else (10 if (nr + r) % 2 else 0))      # default: mix the tiled and the direct kernel
                     grids.append(g)
                     ys.append(crd.NVector.from_numpy(ctx, y[2 * nx * js: 2 * nx * (je + 1)], 2 * nx * ny))
                     ds.append(g.new_vector())
@@ -201,6 +204,95 @@ def test_phi_split_is_bitwise_invariant(crd, ctx, oracle):
                 ctx.sync()
                 for g in grids:
                     g.close()
+
+
+@pytest.mark.parametrize("variant", [13, 15, 20, 21, 0])
+def test_exchange_inside_the_launch(crd, oracle, variant):
+    """crd_rhs on a connected grid: ONE launch per evaluation — its first CTAs push the boundary rows to the neighbours, the
+    tiles / row segments that touch a ghost row come last and acquire their strip's flag.  Two and three ranks emulated on one
+    GPU, each with its own context (stream), so the launches run concurrently and really wait for each other; plain states
+    and fused stage states (their combination is what gets pushed); several epochs through the double-buffered ghost rows.
+    Gathered result bit-identical to the single slab."""
+    model, nx, ny = "fhn_torus", 520, 1400
+    y = oracle.fill_state(model, 2 * nx * ny, seed=5)
+    x2 = oracle.fill_state(model, 2 * nx * ny, seed=6)
+    c0 = crd.Context(0)
+    one = gpu_rhs(crd, c0, model, nx, ny, 10.0, y, crd.ARITH_EXACT, t_boundary=38.0)
+    one50 = gpu_rhs(crd, c0, model, nx, ny, 50.0, y, crd.ARITH_EXACT, t_boundary=38.0)
+    g1 = crd.Grid(c0, crd.make_params(model, nx, ny, t_boundary=38.0))
+    Y1, X1, D1 = crd.NVector.from_numpy(c0, y), crd.NVector.from_numpy(c0, x2), g1.new_vector()
+    g1.f_lincomb(50.0, [1.0, 0.01], [Y1, X1], D1)
+    one_lc = D1.to_numpy()
+    g1.close()
+    for nr in (2, 3):
+        ctxs = [crd.Context(0) for _ in range(nr)]
+        grids, ys, xs, ds = [], [], [], []
+        for r in range(nr):
+            ctxs[r].set_halo_timeout(20000.0)
+            js, je = crd.decomp_phi(ny, nr, r)
+            g = crd.Grid(ctxs[r], crd.make_params(model, nx, ny, js=js, je=je, t_boundary=38.0))
+            g.set_variant(variant)
+            grids.append(g)
+            ys.append(crd.NVector.from_numpy(ctxs[r], y[2 * nx * js: 2 * nx * (je + 1)], 2 * nx * ny))
+            xs.append(crd.NVector.from_numpy(ctxs[r], x2[2 * nx * js: 2 * nx * (je + 1)], 2 * nx * ny))
+            ds.append(g.new_vector())
+        for r in range(nr):
+            grids[r].halo_connect_local(grids[(r - 1) % nr], grids[(r + 1) % nr])
+        for t, want in ((10.0, one), (50.0, one50), (10.0, one), (10.0, one), (50.0, one50)):
+            l0 = [c.launches for c in ctxs]
+            for r in range(nr):
+                grids[r].f(t, ys[r], ds[r])           # asynchronous: every rank's launch is in flight before anyone is waited for
+            for c in ctxs:
+                c.sync()
+            if variant != 0:                          # (0 = automatic: this mesh takes the direct kernel and the separate launches)
+                assert [c.launches - a for c, a in zip(ctxs, l0)] == [1] * nr
+            got = np.concatenate([d.to_numpy() for d in ds])
+            assert got.tobytes() == want.tobytes(), (variant, nr, t)
+        if variant in (13, 20, 21, 0):
+            for r in range(nr):
+                grids[r].f_lincomb(50.0, [1.0, 0.01], [ys[r], xs[r]], ds[r])
+            for c in ctxs:
+                c.sync()
+            assert np.concatenate([d.to_numpy() for d in ds]).tobytes() == one_lc.tobytes(), (variant, nr)
+        for g in grids:
+            g.close()
+        for c in ctxs:
+            c.close()
+    c0.close()
+
+
+def test_a_neighbour_that_never_posts_fails_the_run_instead_of_hanging_or_integrating_on(crd):
+    """A rank of a phi split whose neighbour has died: the wait for its boundary rows gives up after the halo timeout, the
+    evaluation finishes with stale rows — and must not be used: the next wait for the stream reports it, the context stays
+    failed, crd_f returns -1 and ARKode ends with ARK_RHSFUNC_FAIL (the reference would hang in MPI_Wait,
+    FHNmodel_torus.cpp:904-946).  Both ways of running the exchange (inside the launch, as separate launches)."""
+    nx, ny = 300, 1100
+    for variant in (13, 1):
+        ca, cb = crd.Context(0), crd.Context(0)
+        ca.set_halo_timeout(300.0)
+        js, je = crd.decomp_phi(ny, 2, 0)
+        ga = crd.Grid(ca, crd.make_params("fhn_torus", nx, ny, js=js, je=je))
+        js, je = crd.decomp_phi(ny, 2, 1)
+        gb = crd.Grid(cb, crd.make_params("fhn_torus", nx, ny, js=js, je=je))      # never evaluates anything
+        ga.halo_connect_local(gb, gb)
+        ga.set_variant(variant)
+        y, d = ga.new_vector(), ga.new_vector()
+        ga.fill_synthetic(y)
+        assert ca.failed == 0
+        s = crd.ARKodeSolver(ga, y, fused="full", resident=False)
+        flag, _ = s.ARKode(1.0)
+        assert flag < 0, flag                      # ARK_FIRST_RHSFUNC_ERR / ARK_RHSFUNC_FAIL, never success
+        assert ca.failed in (100, 101, 102, 103, 104, 105)
+        with pytest.raises(crd.CrdError):
+            ca.sync()
+        with pytest.raises(crd.CrdError):
+            ga.f(0.0, y, d)                        # sticky: nothing runs on a failed context
+        with pytest.raises(crd.CrdError):
+            ga.new_vector()
+        assert not np.isfinite(crd.N_VWrmsNorm(y, y))
+        ca.clear_error()
+        assert ca.failed == 0 and np.isfinite(crd.N_VMaxNorm(y))
+        s.free(); ga.close(); gb.close(); ca.close(); cb.close()
 
 
 def test_host_entry_matches_device_entry(crd, ctx, oracle):
