@@ -6,6 +6,9 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # CRD_B200_LIB: another build of the same library (kernel experiments); there is still no fallback of any kind
 LIB_PATH = os.environ.get("CRD_B200_LIB") or os.path.join(HERE, "lib", "libcrd_b200.so")
+# the explicit RK driver + generic N_VXxx dispatchers live in their own host-only library (so that linking the real SUNDIALS
+# beside libcrd_b200.so never defines ARKode twice); beside whichever libcrd_b200.so is loaded
+ARK_LIB_PATH = os.environ.get("CRD_ARK_LIB") or os.path.join(os.path.dirname(LIB_PATH), "libcrd_ark.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_long_p = C.POINTER(C.c_long)
@@ -191,22 +194,50 @@ SIGNATURES = {
 _lib = None
 
 
-def bind(handle, signatures=SIGNATURES):
+class _Libs:
+    """Both libraries behind one namespace: libcrd_b200.so (device path, include/crd_b200.h) and libcrd_ark.so (ARKode-legacy
+    names, generic N_VXxx; include/crd_sundials_compat.h, crd_ark.h)."""
+
+    def __init__(self, handles):
+        self._handles = handles
+
+    def __getattr__(self, name):
+        for h in self._handles:
+            try:
+                fn = getattr(h, name)
+            except AttributeError:
+                continue
+            setattr(self, name, fn)
+            return fn
+        raise AttributeError(name)
+
+
+def which_library(name):
+    """'b200' / 'ark': the library that exports `name` (tests)."""
+    L = lib()
+    for tag, h in zip(("b200", "ark"), L._handles):
+        if hasattr(h, name):
+            return tag
+    return None
+
+
+def bind(libs, signatures=SIGNATURES):
     for name, (res, args) in signatures.items():
-        fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+        fn = getattr(libs, name)  # AttributeError if neither library exports the symbol
         fn.restype = res
         fn.argtypes = args
-    return handle
+    return libs
 
 
 def lib():
-    """The loaded library.  Raises CrdError if it has not been built (python -m crdmodel_b200.build)."""
+    """The loaded libraries.  Raises CrdError if they have not been built (python -m crdmodel_b200.build)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise CrdError("%s is missing: build it with `python -m crdmodel_b200.build` "
-                           "(there is no CPU fallback)" % LIB_PATH)
-        _lib = bind(C.CDLL(LIB_PATH))
+        for p in (LIB_PATH, ARK_LIB_PATH):
+            if not os.path.exists(p):
+                raise CrdError("%s is missing: build it with `python -m crdmodel_b200.build` "
+                               "(there is no CPU fallback)" % p)
+        _lib = bind(_Libs([C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL), C.CDLL(ARK_LIB_PATH, mode=C.RTLD_GLOBAL)]))
     return _lib
 
 

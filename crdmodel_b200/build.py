@@ -1,4 +1,9 @@
-"""Build libcrd_b200.so (sm_100a CUDA kernels + C ABI + host integrator) in-tree with nvcc.
+"""Build the two libraries in-tree:
+  libcrd_b200.so  sm_100a CUDA kernels + the C ABI of include/crd_b200.h (nvcc)
+  libcrd_ark.so   the explicit RK driver behind the ARKode-legacy names and the generic N_VXxx dispatchers
+                  (include/crd_sundials_compat.h, crd_ark.h; host-only, g++).  Kept OUT of libcrd_b200.so so that a program
+                  which links the real SUNDIALS 2.x (option A) never sees two definitions of ARKode /
+                  N_VLinearSum; programs without SUNDIALS (option B, the drivers here) link both.
 
     python -m crdmodel_b200.build        # or crdmodel_b200.build.build()
 
@@ -14,6 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libcrd_b200.so")
+LIB_ARK = os.path.join(LIB_DIR, "libcrd_ark.so")
 
 CUDA_SOURCES = ["csrc/crd_ctx.cu", "csrc/crd_rhs.cu", "csrc/crd_nvector.cu", "csrc/crd_resident.cu", "csrc/crd_snapshot.cu"]
 HOST_SOURCES = ["host/crd_ark.cpp", "host/crd_nvector_generic.c"]
@@ -30,24 +36,40 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def _stale(target, sources):
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(HERE, s)) > t for s in CUDA_SOURCES + HOST_SOURCES + HEADERS)
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(os.path.join(HERE, s)) > t for s in sources)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
+def needs_build():
+    return _stale(LIB, CUDA_SOURCES + HEADERS) or _stale(LIB_ARK, HOST_SOURCES + HEADERS[-2:])
+
+
+def build(force=False, verbose=False, profiling_variants=False):
+    """profiling_variants: also compile the tilings that measured slower (-DCRD_PROFILING_VARIANTS; profiles/README.md)."""
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "csrc"),
-                                    "-o", LIB] + [os.path.join(HERE, s) for s in CUDA_SOURCES + HOST_SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "csrc")]
+    if force or profiling_variants or _stale(LIB, CUDA_SOURCES + HEADERS):
+        cmd = [_nvcc()] + NVCC_FLAGS + inc + (["-DCRD_PROFILING_VARIANTS"] if profiling_variants else []) + \
+              ["-o", LIB] + [os.path.join(HERE, s) for s in CUDA_SOURCES]
+        if verbose:
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    if force or _stale(LIB_ARK, HOST_SOURCES + HEADERS[-2:]):
+        objs = []
+        for src in HOST_SOURCES:
+            obj = os.path.join(LIB_DIR, os.path.basename(src) + ".o")
+            cc = ["g++", "-std=c++17"] if src.endswith(".cpp") else ["gcc", "-std=c99"]
+            subprocess.run(cc + ["-O2", "-ffp-contract=off", "-fPIC", "-c", os.path.join(HERE, src), "-o", obj] + inc, check=True)
+            objs.append(obj)
+        cmd = ["g++", "-shared", "-Wl,-Bsymbolic", "-o", LIB_ARK] + objs + ["-lm"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
     return LIB
 
 
@@ -60,13 +82,13 @@ def build_drivers(verbose=False):
     os.makedirs(os.path.join(ROOT, "bin"), exist_ok=True)
     for name, model in (("FHNmodel_torus", 0), ("GoldbeterModel_torus", 1), ("FHNmodel_flat", 2), ("GoldbeterModel_flat", 3)):
         exe = os.path.join(ROOT, "bin", name)
-        deps = [src, LIB] + [os.path.join(HERE, "host", h) for h in ("crd_ini.hpp", "crd_writer.hpp", "crd_workers.hpp", "crd_steady.hpp")]
+        deps = [src, LIB, LIB_ARK] + [os.path.join(HERE, "host", h) for h in ("crd_ini.hpp", "crd_writer.hpp", "crd_workers.hpp", "crd_steady.hpp")]
         if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(d) for d in deps):
             out.append(exe)
             continue
         cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-DCRD_DRIVER_MODEL=%d" % model,
                "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "host"), src, "-o", exe,
-               "-L" + LIB_DIR, "-lcrd_b200", "-Wl,-rpath,$ORIGIN/../crdmodel_b200/lib", "-lpthread", "-lrt"]
+               "-L" + LIB_DIR, "-lcrd_ark", "-lcrd_b200", "-Wl,-rpath,$ORIGIN/../crdmodel_b200/lib", "-lpthread", "-lrt"]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
@@ -75,6 +97,6 @@ def build_drivers(verbose=False):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    build(force="--force" in sys.argv, verbose=True, profiling_variants="--profiling-variants" in sys.argv)
     build_drivers(verbose=True)
     print(LIB)

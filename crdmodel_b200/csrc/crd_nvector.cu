@@ -397,7 +397,9 @@ __global__ void __launch_bounds__(kRedThreads) erk_finish_kernel(const FinishArg
     finish_elem<SEQ, S>(a, a.yn[n - 1], f, o, acc);
     a.ynew[n - 1] = o;
   }
-  block_finish_dd<true>(acc.e_hi, acc.e_lo, acc.y2, partial, ticket, result);
+  // the second sum, or (skipped: crd_fused.cuh, finish_y2_bound) its bound, contributed once
+  const double y2 = a.y2_bound < 0.0 ? acc.y2 : ((blockIdx.x == 0 && threadIdx.x == 0) ? a.y2_bound : 0.0);
+  block_finish_dd<true>(acc.e_hi, acc.e_lo, y2, partial, ticket, result);
 }
 
 struct _generic_N_Vector_Ops g_ops = {
@@ -603,6 +605,7 @@ static int erk_finish_impl(bool seq, int s, const realtype *hb, const realtype *
       if ((uintptr_t)a.F[j] & 15) { set_error("N_VErkFinish_Crd: vectors must be 16-byte aligned"); return -1; }
     }
     a.yn = D(yn); a.ynew = D(ynew); a.rtol = rtol; a.atol = atol;
+    a.hb_nz = finish_nz_mask(hb, s); a.y2_bound = finish_y2_bound(rtol, len);
     if (((uintptr_t)a.yn | (uintptr_t)a.ynew) & 15) { set_error("N_VErkFinish_Crd: vectors must be 16-byte aligned"); return -1; }
     unsigned int blocks = grid_for((len + 1) / 2, c->sms);
     if (blocks > (unsigned)kRedBlocks) blocks = kRedBlocks;

@@ -210,6 +210,7 @@ __device__ __forceinline__ void phase2_rows(const PassCfg &c, const RhsConst &k_
   if (c.ty >= c.G) return;
   const int nx = c.nx, rows = c.rows;
   const int S = FIN ? fin->s : 0;
+  const bool want_y2 = FIN && !(fin->rtol > 2.220446049250313e-16);   // (crd_fused.cuh: finish_y2_bound)
   const RhsConst k = k_in;   // registers: a generic store may alias shared memory, which would force a reload per row
   for (int i = c.tx; i < nx; i += c.ncol) {
     const int iw = (i == 0) ? nx - 1 : i - 1, ie = (i == nx - 1) ? 0 : i + 1;   // theta wraps
@@ -242,13 +243,14 @@ __device__ __forceinline__ void phase2_rows(const PassCfg &c, const RhsConst &k_
         for (int j = 0; j < kResStages; ++j) {
           if (j < S) {
             const double2 fj = (j == S - 1) ? make_double2(du, dv) : fin->F[j][p];
-            sx = fin_sol_term<EXACT>(fin->hb[j], fj.x, sx); ex = fin_err_term<EXACT>(fin->hd[j], fj.x, ex);
-            sy = fin_sol_term<EXACT>(fin->hb[j], fj.y, sy); ey = fin_err_term<EXACT>(fin->hd[j], fj.y, ey);
+            const bool nz = fin->hb[j] != 0.0;
+            sx = fin_sol_term<EXACT>(fin->hb[j], fj.x, sx, nz); ex = fin_err_term<EXACT>(fin->hd[j], fj.x, ex);
+            sy = fin_sol_term<EXACT>(fin->hb[j], fj.y, sy, nz); ey = fin_err_term<EXACT>(fin->hd[j], fj.y, ey);
           }
         }
         fin->ynew[p] = make_double2(sx, sy);
-        finish_tail<EXACT>(fin->rtol, fin->atol, y0.x, sx, ex, facc);
-        finish_tail<EXACT>(fin->rtol, fin->atol, y0.y, sy, ey, facc);
+        finish_tail<EXACT>(fin->rtol, fin->atol, y0.x, sx, ex, facc, want_y2);
+        finish_tail<EXACT>(fin->rtol, fin->atol, y0.y, sy, ey, facc, want_y2);
       }
     }
   }
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(NT, 1) erk_resident_kernel(const ResArgs P) {
               L.eta = eta_a;
               if (dsm <= 1.0) {
                 L.eh1 = L.eh0; L.eh0 = dsm * P.bias;
-                L.ynorm_sq = sy;
+                L.ynorm_sq = P.rtol > 2.220446049250313e-16 ? P.nglobal / (P.rtol * P.rtol) : sy;   // the bound when the sum is skipped
                 L.status = 1;
                 // complete the step: yn <- ynew (ping-pong); fnew goes into the other F storage
                 L.yi ^= 1;

@@ -314,6 +314,7 @@ int crd_rhs_lincomb_finish(crd_grid *g, double t, int s, const double *c, const 
   FinCtx fc;
   for (int j = 0; j < kMaxLc; ++j) { fc.fin.hb[j] = hb[j]; fc.fin.hd[j] = hd[j]; }
   fc.fin.rtol = rtol; fc.fin.atol = atol; fc.fin.partial = g->fin_partial;
+  fc.fin.hb_nz = finish_nz_mask(hb, s); fc.fin.y2_bound = finish_y2_bound(rtol, g->nx * g->nyl * 2);
   if (compute_state(g, t, S, ynew_dev, false, &fc)) return -1;
   // add the per-CTA sums in a fixed order
   // ... and, with the device-side allreduce wired, exchange them with the other ranks in the same launch

@@ -419,6 +419,8 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 struct StageFin {
   double hb[kMaxLc], hd[kMaxLc];
   double rtol, atol;
+  unsigned hb_nz;    // bit j: hb[j] != 0
+  double y2_bound;   // >= 0: the second sum is skipped and this bound reported instead (crd_fused.cuh: finish_y2_bound)
   double *partial;   // [3][kRedBlocks] per-CTA sums: error sum hi | sum (ynew w')^2 | error sum lo
 };
 
@@ -504,6 +506,7 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
   int slot_i = 0;
   unsigned slot_par = 0;
   FinAcc<EXACT> facc;   // FIN: this thread's share of sum (err w)^2 (double-double when EXACT), sum (ynew w')^2
+  const bool want_y2 = FIN && fz.y2_bound < 0.0, nz_last = (fz.hb_nz >> (NV - 1)) & 1u;
   double lcc[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) lcc[j] = a.lc_c[j];
@@ -574,12 +577,12 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
       if constexpr (!FIN) {
         if (active) *out = make_double2(du, dv);
       } else if constexpr (FIN == 2) {
-        const double sx = fin_sol_term<EXACT>(fz.hb[NV - 1], du, psum.x), ex = fin_err_term<EXACT>(fz.hd[NV - 1], du, perr.x);
-        const double sy = fin_sol_term<EXACT>(fz.hb[NV - 1], dv, psum.y), ey = fin_err_term<EXACT>(fz.hd[NV - 1], dv, perr.y);
+        const double sx = fin_sol_term<EXACT>(fz.hb[NV - 1], du, psum.x, nz_last), ex = fin_err_term<EXACT>(fz.hd[NV - 1], du, perr.x);
+        const double sy = fin_sol_term<EXACT>(fz.hb[NV - 1], dv, psum.y, nz_last), ey = fin_err_term<EXACT>(fz.hd[NV - 1], dv, perr.y);
         if (active) {
           *out = make_double2(sx, sy);
-          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].x, sx, ex, facc);
-          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].y, sy, ey, facc);
+          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].x, sx, ex, facc, want_y2);
+          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].y, sy, ey, facc, want_y2);
         }
       } else {
         // ynew = yn + sum_j hb_j F_j, err = sum_j hd_j F_j with F_{NV-1} = (du, dv): the operation order of finish_elem
@@ -587,13 +590,14 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
           const double2 f = (j == NV - 1) ? make_double2(du, dv) : pv[j + 1 < NV ? j + 1 : 0];
-          sx = fin_sol_term<EXACT>(fz.hb[j], f.x, sx); ex = fin_err_term<EXACT>(fz.hd[j], f.x, ex);
-          sy = fin_sol_term<EXACT>(fz.hb[j], f.y, sy); ey = fin_err_term<EXACT>(fz.hd[j], f.y, ey);
+          const bool nz = (fz.hb_nz >> j) & 1u;
+          sx = fin_sol_term<EXACT>(fz.hb[j], f.x, sx, nz); ex = fin_err_term<EXACT>(fz.hd[j], f.x, ex);
+          sy = fin_sol_term<EXACT>(fz.hb[j], f.y, sy, nz); ey = fin_err_term<EXACT>(fz.hd[j], f.y, ey);
         }
         if (active) {
           *out = make_double2(sx, sy);
-          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].x, sx, ex, facc);
-          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].y, sy, ey, facc);
+          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].x, sx, ex, facc, want_y2);
+          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].y, sy, ey, facc, want_y2);
         }
       }
       out += nx;
@@ -612,8 +616,9 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
 #pragma unroll
           for (int j = 0; j < NV - 1; ++j) {
             const double2 f = lds_f64x2(sa + (unsigned)((j + 1) * PITCH * 16));
-            psum.x = fin_sol_term<EXACT>(fz.hb[j], f.x, psum.x); perr.x = fin_err_term<EXACT>(fz.hd[j], f.x, perr.x);
-            psum.y = fin_sol_term<EXACT>(fz.hb[j], f.y, psum.y); perr.y = fin_err_term<EXACT>(fz.hd[j], f.y, perr.y);
+            const bool nz = (fz.hb_nz >> j) & 1u;
+            psum.x = fin_sol_term<EXACT>(fz.hb[j], f.x, psum.x, nz); perr.x = fin_err_term<EXACT>(fz.hd[j], f.x, perr.x);
+            psum.y = fin_sol_term<EXACT>(fz.hb[j], f.y, psum.y, nz); perr.y = fin_err_term<EXACT>(fz.hd[j], f.y, perr.y);
           }
         }
       }
@@ -660,6 +665,7 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
     if (threadIdx.x == 0) {
       double sh = fin_red[0][0], sy = fin_red[1][0], sl = fin_red[2][0];
       for (int w = 1; w < 8; ++w) { dd_merge(sh, sl, fin_red[0][w], fin_red[2][w]); sy += fin_red[1][w]; }
+      if (!want_y2) sy = blockIdx.x == 0 ? fz.y2_bound : 0.0;   // the launch's bound, once
       fz.partial[blockIdx.x] = sh;
       fz.partial[kRedBlocks + blockIdx.x] = sy;
       fz.partial[2 * kRedBlocks + blockIdx.x] = sl;

@@ -11,7 +11,10 @@
  *   rhs_lincomb ydot = f(t, sum_j c[j] X[j])  (stage assembly fused into the right-hand side)
  *   erk_finish  ynew = yn + sum_j hb[j] F[j];  err = sum_j hd[j] F[j];
  *               out[0] = sum_global (err_i  * w_i )^2,  w_i  = 1/(rtol |yn_i|   + atol)
- *               out[1] = sum_global (ynew_i * w'_i)^2,  w'_i = 1/(rtol |ynew_i| + atol)
+ *               out[1] = sum_global (ynew_i * w'_i)^2,  w'_i = 1/(rtol |ynew_i| + atol): the norm of the new state, which only
+ *                        ever feeds the "too much accuracy" test uround * sqrt(out[1] / N) > 1.  Every term is below
+ *                        1 / rtol^2, so for rtol > uround the test cannot fire; an implementation may then report the
+ *                        bound N / rtol^2 instead of forming the sum (the device kernels do).
  *               (the error weights are a pure function of the state, so no ewt vector is stored).
  *   rhs_lincomb_finish  the LAST stage evaluation and erk_finish in one pass (the stage derivative is never stored)
  *   erk_evolve  the whole adaptive step loop (stages, finish, error test, step controller) inside ONE persistent

@@ -8,9 +8,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_functions():
+def declared_functions(headers=("crd_b200.h", "crd_ark.h", "crd_sundials_compat.h")):
     names = set()
-    for h in ("crd_b200.h", "crd_ark.h", "crd_sundials_compat.h"):
+    for h in headers:
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         src = re.sub(r'extern\s+"C"\s*\{', "", src)
@@ -32,11 +32,44 @@ def declared_functions():
 
 
 def test_header_symbols_exported(crd):
-    handle = C.CDLL(crd.LIB_PATH)
-    names = declared_functions()
-    assert len(names) > 100
-    missing = [n for n in names if not hasattr(handle, n)]
-    assert not missing, missing
+    """include/crd_b200.h -> libcrd_b200.so (the device path); include/crd_sundials_compat.h + crd_ark.h (the ARKode-legacy
+    names, the generic N_VXxx dispatchers, the RK driver's extensions) -> libcrd_ark.so, and ONLY there: a program that links
+    the real SUNDIALS 2.x beside libcrd_b200.so (option A) must never see ARKode or N_VLinearSum twice."""
+    from crdmodel_b200 import _lib
+    b200, ark = C.CDLL(_lib.LIB_PATH), C.CDLL(_lib.ARK_LIB_PATH)
+    dev = declared_functions(("crd_b200.h",))
+    host = sorted(set(declared_functions(("crd_ark.h", "crd_sundials_compat.h"))))
+    assert len(dev) > 90 and len(host) > 40
+    dev_only = [n for n in dev if n not in host]
+    assert not [n for n in dev_only if not hasattr(b200, n)]
+    assert not [n for n in host if not hasattr(ark, n)]
+    assert not [n for n in host if hasattr(b200, n)], "libcrd_b200.so must not define SUNDIALS' names"
+
+
+def test_sundials_names_bind_to_whatever_the_program_links(crd, tmp_path):
+    """Option A of INTEGRATION.md in miniature: a library standing in for libsundials_arkode / libsundials_nvecparallel
+    defines ARKodeCreate and N_VLinearSum; a program linked against it AND libcrd_b200.so gets the stand-in's, whatever the
+    link order."""
+    import subprocess
+    from crdmodel_b200 import build as B
+    inc = os.path.join(ROOT, "include")
+    stub = tmp_path / "stub.c"
+    stub.write_text('#include "crd_sundials_compat.h"\nstatic int marker = 4242;\n'
+                    'void *ARKodeCreate(void) { return &marker; }\n'
+                    'void N_VLinearSum(realtype a, N_Vector x, realtype b, N_Vector y, N_Vector z) { (void)a; (void)x; (void)b; (void)y; (void)z; marker = 17; }\n'
+                    'int stub_marker(void) { return marker; }\n')
+    subprocess.run(["gcc", "-std=c99", "-shared", "-fPIC", "-I" + inc, str(stub), "-o", str(tmp_path / "libstub.so")], check=True)
+    prog = tmp_path / "prog.c"
+    prog.write_text('#include "crd_b200.h"\nint stub_marker(void);\n'
+                    'int main(void) { int *m = (int *)ARKodeCreate(); if (!m || *m != 4242) return 1;\n'
+                    '  N_VLinearSum(1.0, 0, 1.0, 0, 0); if (stub_marker() != 17) return 2;\n'
+                    '  return crd_device_count() >= 0 ? 0 : 3; }\n')
+    for order in (["-lstub", "-lcrd_b200"], ["-lcrd_b200", "-lstub"]):
+        exe = tmp_path / "prog"
+        subprocess.run(["gcc", "-std=c99", "-I" + inc, str(prog), "-o", str(exe), "-L" + str(tmp_path), "-L" + B.LIB_DIR] + order +
+                       ["-Wl,-rpath," + str(tmp_path), "-Wl,-rpath," + B.LIB_DIR], check=True)
+        r = subprocess.run([str(exe)], capture_output=True, text=True)
+        assert r.returncode == 0, (order, r.returncode, r.stderr)
 
 
 def test_binding_covers_header(crd):
@@ -93,7 +126,7 @@ def test_headers_are_plain_c(tmp_path):
                    '  void *m = ARKodeCreate(); if (!m) return 2; ARKodeFree(&m);\n'
                    '  printf("%d\\n", crd_device_count()); return 0; }\n')
     exe = tmp_path / "use"
-    subprocess.run(["gcc", "-std=c99", "-I" + inc, str(src), "-o", str(exe), "-L" + B.LIB_DIR, "-lcrd_b200",
+    subprocess.run(["gcc", "-std=c99", "-I" + inc, str(src), "-o", str(exe), "-L" + B.LIB_DIR, "-lcrd_ark", "-lcrd_b200",
                     "-Wl,-rpath," + B.LIB_DIR], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stderr)
