@@ -23,8 +23,8 @@ LIB_ARK = os.path.join(LIB_DIR, "libcrd_ark.so")
 
 CUDA_SOURCES = ["csrc/crd_ctx.cu", "csrc/crd_rhs.cu", "csrc/crd_nvector.cu", "csrc/crd_resident.cu", "csrc/crd_snapshot.cu"]
 HOST_SOURCES = ["host/crd_ark.cpp", "host/crd_nvector_generic.c"]
-HEADERS = ["csrc/crd_common.cuh", "csrc/crd_grid.cuh", "csrc/crd_rhs_kernels.cuh", "csrc/crd_rhs_point.cuh", "csrc/crd_fused.cuh", "csrc/crd_tables.hpp", "../include/crd_b200.h", "../include/crd_ark.h",
-           "../include/crd_sundials_compat.h"]
+HEADERS = ["csrc/crd_common.cuh", "csrc/crd_grid.cuh", "csrc/crd_rhs_kernels.cuh", "csrc/crd_rhs_point.cuh", "csrc/crd_fused.cuh", "csrc/crd_tables.hpp", "../include/crd_b200.h",
+           "host/crd_pow.h", "../include/crd_ark.h", "../include/crd_sundials_compat.h"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "--threads", "4", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "-Xlinker", "-Bsymbolic", "-shared"]
 
@@ -44,7 +44,7 @@ def _stale(target, sources):
 
 
 def needs_build():
-    return _stale(LIB, CUDA_SOURCES + HEADERS) or _stale(LIB_ARK, HOST_SOURCES + HEADERS[-2:])
+    return _stale(LIB, CUDA_SOURCES + HEADERS) or _stale(LIB_ARK, HOST_SOURCES + HEADERS[-3:])
 
 
 def build(force=False, verbose=False, profiling_variants=False):
@@ -59,7 +59,7 @@ def build(force=False, verbose=False, profiling_variants=False):
             cmd.insert(2, "-v")
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
-    if force or _stale(LIB_ARK, HOST_SOURCES + HEADERS[-2:]):
+    if force or _stale(LIB_ARK, HOST_SOURCES + HEADERS[-3:]):
         objs = []
         for src in HOST_SOURCES:
             obj = os.path.join(LIB_DIR, os.path.basename(src) + ".o")

@@ -31,6 +31,7 @@
 
 #include "crd_fused.cuh"
 #include "crd_rhs_point.cuh"
+#include "../host/crd_pow.h"
 
 namespace {
 
@@ -262,7 +263,7 @@ __device__ double res_adapt_eta(const ResArgs &P, double hcur, double dsm, doubl
   const double k = (double)P.p;
   const double base = lane == 0 ? fmax(P.bias * dsm, 1.0e-10) : lane == 1 ? fmax(eh0, 1.0e-10) : fmax(eh1, 1.0e-10);
   const double expo = lane == 0 ? -P.k1 / k : lane == 1 ? P.k2 / k : -P.k3 / k;
-  const double pw = pow(base, expo);
+  const double pw = crd_pow_pos(base, expo);   // the host controller's own sequence of operations (crd_pow.h): same bits
   const double p1 = __shfl_sync(0xffffffffu, pw, 0), p2 = __shfl_sync(0xffffffffu, pw, 1), p3 = __shfl_sync(0xffffffffu, pw, 2);
   double h_acc = hcur * p1 * p2 * p3;
   const double int_dir = hcur / fabs(hcur);

@@ -25,6 +25,7 @@
 #include <new>
 
 #include "crd_ark.h"
+#include "crd_pow.h"
 
 namespace {
 
@@ -194,7 +195,9 @@ double adapt_eta(ArkMem *m, double dsm) {
   double e1 = std::max(m->bias * dsm, TINY);
   double e2 = std::max(m->ehist[0], TINY);
   double e3 = std::max(m->ehist[1], TINY);
-  double h_acc = hcur * std::pow(e1, -m->k1 / k) * std::pow(e2, m->k2 / k) * std::pow(e3, -m->k3 / k);
+  // crd_pow_pos: x^y as one fixed sequence of IEEE operations, so that the device-resident loop (which runs this controller
+  // inside its kernel) chooses the same step sizes bit for bit (libm's and CUDA's pow differ in the last place)
+  double h_acc = hcur * crd_pow_pos(e1, -m->k1 / k) * crd_pow_pos(e2, m->k2 / k) * crd_pow_pos(e3, -m->k3 / k);
   double int_dir = hcur / std::fabs(hcur);
   h_acc *= m->safety;
   h_acc = int_dir * std::min(std::fabs(h_acc), std::fabs(m->etamax * hcur));

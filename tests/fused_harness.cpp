@@ -43,7 +43,7 @@ double fh_lc(int seq, int n, const double *c, const double *v) {
 
 // the finish over n elements: ynew[i], and the three sums (error hi / lo, second norm)
 void fh_finish(int seq, int S, const double *hb, const double *hd, double rtol, double atol, long n, const double *yn,
-               const double *F /* [S][n] */, double *ynew, double *sums /* [3] */) {
+               const double *F /* [S][n] */, double *ynew, double *sums /* [3] */, int want_y2) {
   FinishArgs a;
   for (int j = 0; j < S; ++j) { a.hb[j] = hb[j]; a.hd[j] = hd[j]; }
   a.rtol = rtol; a.atol = atol;
@@ -53,12 +53,12 @@ void fh_finish(int seq, int S, const double *hb, const double *hd, double rtol, 
     double s = yn[i], err = 0.0;
     for (int j = 0; j < S; ++j) {
       const double f = F[(long)j * n + i];
-      if (seq) { s = fin_sol_term<true>(a.hb[j], f, s); err = fin_err_term<true>(a.hd[j], f, err); }
-      else { s = fin_sol_term<false>(a.hb[j], f, s); err = fin_err_term<false>(a.hd[j], f, err); }
+      if (seq) { s = fin_sol_term<true>(a.hb[j], f, s, a.hb[j] != 0.0); err = fin_err_term<true>(a.hd[j], f, err); }
+      else { s = fin_sol_term<false>(a.hb[j], f, s, a.hb[j] != 0.0); err = fin_err_term<false>(a.hd[j], f, err); }
     }
     ynew[i] = s;
-    if (seq) finish_tail<true>(rtol, atol, yn[i], s, err, at);
-    else finish_tail<false>(rtol, atol, yn[i], s, err, af);
+    if (seq) finish_tail<true>(rtol, atol, yn[i], s, err, at, want_y2 != 0);
+    else finish_tail<false>(rtol, atol, yn[i], s, err, af, want_y2 != 0);
   }
   sums[0] = seq ? at.e_hi : af.e_hi; sums[1] = seq ? at.y2 : af.y2; sums[2] = seq ? at.e_lo : af.e_lo;
 }

@@ -270,3 +270,29 @@ def test_evolve_hook_failures_are_reported_like_the_host_loop(K):
     assert flags == [-1] and ts == [0.0] and st["nst"] == 5 and outs[0].tolist() == [1.0, 0.0]
     outs, flags, ts, st = integrate_with_evolve(K, f, [1.0, 0.0], [1.0], lambda stp, user: -1)
     assert flags == [-20]       # ARK_MEM_FAIL: the device loop could not be launched
+
+
+def test_controller_pow_is_accurate_and_independent_of_libm(tmp_path):
+    """crd_pow.h: x^y as one fixed sequence of IEEE operations shared by the host controller (crd_ark.cpp) and the device-resident
+    loop (crd_resident.cu), so both choose the same step sizes bit for bit.  Here: accuracy against libm over the controller's
+    domain (bases max(bias*dsm, 1e-10) .. 1e5, exponents -k1/p, k2/p, -k3/p and a few others)."""
+    import ctypes
+    import math
+    import subprocess
+    import numpy as np
+    src = tmp_path / "p.c"
+    src.write_text('#include "crd_pow.h"\ndouble crd_test_pow(double x, double y) { return crd_pow_pos(x, y); }\n')
+    so = tmp_path / "p.so"
+    subprocess.run(["gcc", "-O2", "-std=c99", "-ffp-contract=off", "-fPIC", "-shared", "-I" + os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "crdmodel_b200", "host"),
+                    str(src), "-o", str(so)], check=True)
+    f = ctypes.CDLL(str(so)).crd_test_pow
+    f.restype = ctypes.c_double
+    f.argtypes = [ctypes.c_double, ctypes.c_double]
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for y in (-0.58 / 3, 0.21 / 3, -0.1 / 3, -0.25, 0.5, 1.0, -1.0, 2.0 / 3):
+        for x in np.concatenate([10.0 ** rng.uniform(-10, 5, 4000), [1e-10, 1.0, 2.0, 0.5, 1.5, math.sqrt(2.0), 1e5]]):
+            got, want = f(float(x), y), math.pow(float(x), y)
+            worst = max(worst, abs(got - want) / want)
+    assert worst < 4e-15, worst
+    assert f(1.0, -0.58 / 3) == 1.0 and f(4.0, 0.5) == 2.0

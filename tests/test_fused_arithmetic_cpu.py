@@ -27,7 +27,7 @@ def fh(tmp_path_factory):
     lib = C.CDLL(str(so))
     lib.fh_lc.restype = D
     lib.fh_lc.argtypes = [I, I, P, P]
-    lib.fh_finish.argtypes = [I, I, P, P, D, D, L, P, P, P, P]
+    lib.fh_finish.argtypes = [I, I, P, P, D, D, L, P, P, P, P, I]
     lib.fh_rcp.restype = D
     lib.fh_rcp.argtypes = [D, D]
     lib.fh_rcp_in_range.argtypes = [D]
@@ -77,12 +77,12 @@ def test_step_finish_has_the_bits_of_the_op_by_op_sequence_and_an_exactly_rounde
     ewt = 1.0 / (rtol * np.abs(yn) + atol)
     terms = (tempv * ewt) ** 2
     ynew = np.empty(n); sums = np.empty(3)
-    fh.fh_finish(1, S, hb.ctypes.data, hd.ctypes.data, rtol, atol, n, yn.ctypes.data, F.ctypes.data, ynew.ctypes.data, sums.ctypes.data)
+    fh.fh_finish(1, S, hb.ctypes.data, hd.ctypes.data, rtol, atol, n, yn.ctypes.data, F.ctypes.data, ynew.ctypes.data, sums.ctypes.data, 1)
     assert ynew.tobytes() == ycur.tobytes()
     assert sums[0] + sums[2] == math.fsum(terms)           # double-double sum rounds to the exact sum
     # fused multiply-add arithmetic: same quantities to rounding
     ynew_f = np.empty(n); sums_f = np.empty(3)
-    fh.fh_finish(0, S, hb.ctypes.data, hd.ctypes.data, rtol, atol, n, yn.ctypes.data, F.ctypes.data, ynew_f.ctypes.data, sums_f.ctypes.data)
+    fh.fh_finish(0, S, hb.ctypes.data, hd.ctypes.data, rtol, atol, n, yn.ctypes.data, F.ctypes.data, ynew_f.ctypes.data, sums_f.ctypes.data, 1)
     assert np.abs(ynew_f - ycur).max() <= 1e-15 * (1 + np.abs(ycur).max())
     assert abs(sums_f[0] - math.fsum(terms)) <= 1e-9 * math.fsum(terms)
     assert abs(sums_f[1] - sums[1]) <= 1e-12 * sums[1]
