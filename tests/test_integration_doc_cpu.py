@@ -30,7 +30,7 @@ def test_integration_snippets_compile_against_the_headers(tmp_path):
     body, hook = blocks[0].split("static int mpi_allreduce_hook", 1)
     body = body.replace('#include "crd_b200.h"', "")
     src = (PRELUDE + "void option_a() {\n" + body + "\n}\nstatic int mpi_allreduce_hook" + hook +
-           "\nvoid option_b() {\n" + blocks[1] + "\n}\n")
+           "\nvoid option_b() {\n  crd_grid *grid = 0;   // created as in option A\n" + blocks[1] + "\n}\n")
     f = tmp_path / "integration.cpp"
     f.write_text(src)
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wno-vla", "-I" + os.path.join(ROOT, "include"), str(f)],
