@@ -567,45 +567,61 @@ def main():
 
     extras = not args.no_extras
     # ---- integrator steps/s (fused N_Vector ops + RHS), reported alongside -------------------------------
-    integ = None
+    def integrator_block(g, label):
+        """50 steps of one ARK_NORMAL call (the loop as the drivers run it), then 10 ARK_ONE_STEP calls (each also copies the
+        state into the caller's vector) on grid g from the synthetic state."""
+        g.fill_synthetic(y)
+        solver = crd.ARKodeSolver(g, y, t0=T_EVAL, fused="full", max_steps=50)
+        solver.set_init_step(1e-9)
+        flag, _ = solver.ARKode(T_EVAL + 1.0, crd.ARK_ONE_STEP)   # set-up + first step
+        ctx.sync(); barrier()
+        n0 = solver.stats()
+        t0 = time.time()
+        flag_n, _ = solver.ARKode(T_EVAL + 1.0, crd.ARK_NORMAL)    # returns ARK_TOO_MUCH_WORK (-1) after exactly 50 steps
+        ctx.sync()
+        dt_n = max_over_ranks(time.time() - t0)
+        n1 = solver.stats()
+        t0 = time.time()
+        for _ in range(10):
+            flag, tcur = solver.ARKode(T_EVAL + 1.0, crd.ARK_ONE_STEP)
+            if flag < 0:
+                break
+        ctx.sync()
+        dt_1 = max_over_ranks(time.time() - t0)
+        n2 = solver.stats()
+        solver.free()
+        g.fill_synthetic(y)
+        att = max(1, n1["nst_attempts"] - n0["nst_attempts"])
+        return {"steps_per_s": (n1["nst"] - n0["nst"]) / dt_n, "step_attempts_per_s": att / dt_n, "ms_per_attempt": 1e3 * dt_n / att,
+                "nst": n1["nst"] - n0["nst"], "nfe": n1["nfe"] - n0["nfe"], "netf": n1["netf"] - n0["netf"],
+                "rhs_per_attempt": (n1["nfe"] - n0["nfe"]) / att, "flag": flag_n, "mode": "ARK_NORMAL, 50-step limit (flag -1 = the limit, as intended)",
+                "bytes_per_point_per_attempt": 384, "floor_ms_at_measured_peak": 384 * points / (peaks["hbm_gbs"] * 1e6),
+                "one_step_mode": {"steps_per_s": (n2["nst"] - n1["nst"]) / dt_1, "nst": n2["nst"] - n1["nst"], "flag": flag,
+                                  "note": "ARK_ONE_STEP returns the state in the caller's vector: one more 32 B/point copy per call"},
+                "arith": label}
+
+    integ = integ_fast = None
     if extras and not args.no_integrator:
+        method = ("Zonneveld 5-3-4 explicit RK, rtol 1e-5 atol 1e-10, host-driven loop (mesh beyond L2: the resident loop does not apply), stage "
+                  "assembly fused into the RHS kernels, last stage fused with the step finish, f(tn, yn) of the previous step reused as stage 1 "
+                  "(bit-identical to re-evaluating it as ARKode 1.x does: 5 instead of 6 evaluations per step), norms exchanged between the "
+                  "GPUs on the device")
         try:
-            method = ("Zonneveld 5-3-4 explicit RK, rtol 1e-5 atol 1e-10, host-driven loop (mesh beyond L2: the resident loop does not apply), stage "
-                      "assembly fused into the RHS kernels, last stage fused with the step finish, f(tn, yn) of the previous step reused as stage 1 "
-                      "(bit-identical to re-evaluating it as ARKode 1.x does: 5 instead of 6 evaluations per step)")
-            grid.fill_synthetic(y)
-            solver = crd.ARKodeSolver(grid, y, t0=T_EVAL, fused="full", max_steps=50)
-            solver.set_init_step(1e-9)
-            flag, _ = solver.ARKode(T_EVAL + 1.0, crd.ARK_ONE_STEP)   # set-up + first step
-            ctx.sync(); barrier()
-            # (a) ARK_NORMAL towards a far tout with a 50-step limit: the loop as the drivers run it (no per-step copy of the state)
-            n0 = solver.stats()
-            t0 = time.time()
-            flag_n, _ = solver.ARKode(T_EVAL + 1.0, crd.ARK_NORMAL)    # returns ARK_TOO_MUCH_WORK (-1) after exactly 50 steps
-            ctx.sync()
-            dt_n = max_over_ranks(time.time() - t0)
-            n1 = solver.stats()
-            # (b) ARK_ONE_STEP x 10: every call also copies the state into the caller's vector
-            t0 = time.time()
-            for _ in range(10):
-                flag, tcur = solver.ARKode(T_EVAL + 1.0, crd.ARK_ONE_STEP)
-                if flag < 0:
-                    break
-            ctx.sync()
-            dt_1 = max_over_ranks(time.time() - t0)
-            n2 = solver.stats()
-            att = max(1, n1["nst_attempts"] - n0["nst_attempts"])
-            integ = {"steps_per_s": (n1["nst"] - n0["nst"]) / dt_n, "step_attempts_per_s": att / dt_n, "ms_per_attempt": 1e3 * dt_n / att,
-                     "nst": n1["nst"] - n0["nst"], "nfe": n1["nfe"] - n0["nfe"], "netf": n1["netf"] - n0["netf"],
-                     "rhs_per_attempt": (n1["nfe"] - n0["nfe"]) / att, "flag": flag_n, "mode": "ARK_NORMAL, 50-step limit (flag -1 = the limit, as intended)",
-                     "bytes_per_point_per_attempt": 384, "floor_ms_at_measured_peak": 384 * points / (peaks["hbm_gbs"] * 1e6),
-                     "one_step_mode": {"steps_per_s": (n2["nst"] - n1["nst"]) / dt_1, "nst": n2["nst"] - n1["nst"], "flag": flag,
-                                       "note": "ARK_ONE_STEP returns the state in the caller's vector: one more 32 B/point copy per call"},
-                     "method": method}
-            solver.free()
-            grid.fill_synthetic(y)
+            integ = integrator_block(grid, args.arith + (": every fused kernel reproduces the bits of the op-by-op N_Vector sequence and the error norm is an "
+                                                          "exactly rounded sum; the trajectory is bit-identical to the CPU run's" if args.arith == "exact" else ""))
+            integ["method"] = method
         except Exception as e:  # the headline metric does not depend on this block
             integ = {"error": str(e)[:200]}
+        if args.arith == "exact":
+            # the same loop in FAST arithmetic (fma chains, approximate reciprocal weights; trajectory within rtol |y| + atol)
+            try:
+                gf = crd.Grid(ctx, crd.make_params(model, nx, ny, js=js, je=je, arith=crd.ARITH_FAST))
+                if use_dist:
+                    cdist.ring_connect(gf, rank, world, cdist.exchange_handles(gf.halo_handle(), gloo))
+                integ_fast = integrator_block(gf, "fast: fused multiply-add chains, <= 1e-12 per evaluation, trajectory within the integrator tolerance")
+                gf.close()
+            except Exception as e:
+                integ_fast = {"error": str(e)[:200]}
 
     # ---- the reference's own default meshes (BASELINE configs[1], [2]): whole adaptive integrations ----
     integ_small = None
@@ -686,7 +702,8 @@ def main():
                              "kernel": "rhs_tile_kernel<%s,%s,TX=256,TY=16> (TMA bulk-copy tiles)" % (model.upper(), args.arith), "bytes_per_point": BYTES_PER_POINT,
                              "points_per_launch": points},
                 "parity": parity, "sustained": sustained, "e2e": e2e,
-                "gpu_launches": int(launches), "clocks": clocks, "integrator": integ, "integrator_stage_kernels": stage_kernels,
+                "gpu_launches": int(launches), "clocks": clocks, "integrator": integ, "integrator_fast": integ_fast,
+                "integrator_stage_kernels": stage_kernels,
                 "integrator_default_meshes": integ_small, "cfg5": cfg5}
         if world == 1 and extras and not args.no_cpu_baseline:
             try:

@@ -6,4 +6,4 @@ ctypes mirror.  Importing it never needs a GPU; creating a Context does, and the
 from ._lib import CrdError, IcParams, Params, LIB_PATH, lib  # noqa: F401
 from .api import *  # noqa: F401,F403
 from .api import (ARITH_EXACT, ARITH_FAST, ARK_NORMAL, ARK_ONE_STEP, MODELS, ARKodeSolver, Context, Grid,  # noqa: F401
-                  NVector, decomp_phi, make_params)
+                  NVector, Snapshot, decomp_phi, make_params)

@@ -356,6 +356,50 @@ class Grid:
         self.ctx.fill_synthetic(self.params.model, self.local_length, _ptr(y), seed, 2 * self.js * self.nx)
 
 
+class Snapshot:
+    """Output snapshots off the time loop's critical path (crd_snapshot_*): begin() enqueues a gather of the written
+    variables + an asynchronous copy into a page-locked buffer and returns the slot; wait(slot) blocks until the copy has
+    landed and returns numpy views of the values; release(slot) hands the buffer back."""
+
+    _close_rank = 0
+
+    def __init__(self, ctx, npoints, nvars=1, nslots=2):
+        self.ctx, self.n, self.nvars = ctx, npoints, nvars
+        self._h = check_ptr(lib().crd_snapshot_create(ctx._h, npoints, nvars, nslots), "crd_snapshot_create")
+        ctx._adopt(self)
+
+    def begin(self, y):
+        slot = lib().crd_snapshot_begin(self._h, _ptr(y))
+        if slot == -1:
+            check(slot, "crd_snapshot_begin")
+        return slot          # -2: every slot is still held
+
+    def wait(self, slot):
+        p0, p1 = C.c_void_p(), C.c_void_p()
+        check(lib().crd_snapshot_wait(self._h, slot, C.byref(p0), C.byref(p1)), "crd_snapshot_wait")
+        v0 = np.ctypeslib.as_array(C.cast(p0, C.POINTER(C.c_double)), shape=(self.n,))
+        v1 = np.ctypeslib.as_array(C.cast(p1, C.POINTER(C.c_double)), shape=(self.n,)) if p1.value else None
+        return v0, v1
+
+    def release(self, slot):
+        check(lib().crd_snapshot_release(self._h, slot), "crd_snapshot_release")
+
+    def close(self):
+        if self._h:
+            if self.ctx._h:
+                lib().crd_snapshot_destroy(self._h)
+            self._h = None
+
+    def _release(self):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ARKodeSolver:
     """The reference's ARKode call sequence (FHNmodel_torus.cpp:356-373,423,491) over the device path."""
 

@@ -300,8 +300,11 @@ int crd_f_lincomb(realtype t, int n, const realtype *c, N_Vector *X, N_Vector yd
 int crd_rhs_lincomb_finish(crd_grid *g, double t, int s, const double *c, const double *hb, const double *hd,
                            const double *const *X_dev, double *ynew_dev, double rtol, double atol, double out[2]) {
   if (!g || !c || !hb || !hd || !X_dev || !ynew_dev || !out) { set_error("crd_rhs_lincomb_finish: null argument"); return -1; }
-  // decided before anything is posted to the neighbours: 5 stages, a mesh the streaming kernel is made for
+  // decided before anything is posted to the neighbours: 5 stages, a mesh the streaming kernel is made for, non-zero solution
+  // weights of the stored stages (the kernel adds those terms unconditionally; the op-by-op chain skips zero weights)
   if (s != kMaxLc || g->nx < 192 || g->nx * g->nyl < (1LL << 20)) return 1;
+  for (int j = 0; j + 1 < s; ++j)
+    if (hb[j] == 0.0) return 1;
   crd_ctx *ctx = g->ctx;
   if (use(ctx)) return -1;
   StateRef S;

@@ -505,7 +505,8 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
   const int nxi = (int)nx, nyli = (int)nyl;
   int slot_i = 0;
   unsigned slot_par = 0;
-  FinAcc<EXACT> facc;   // FIN: this thread's share of sum (err w)^2 (double-double when EXACT), sum (ynew w')^2
+  FinAcc<EXACT> facc, faccy;   // FIN: this thread's share of sum (err w)^2 (double-double when EXACT) and sum (ynew w')^2, one
+                               // accumulator per component so that the two dependency chains of a point run side by side
   const bool want_y2 = FIN && fz.y2_bound < 0.0, nz_last = (fz.hb_nz >> (NV - 1)) & 1u;
   double lcc[NV];
 #pragma unroll
@@ -582,7 +583,7 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
         if (active) {
           *out = make_double2(sx, sy);
           finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].x, sx, ex, facc, want_y2);
-          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].y, sy, ey, facc, want_y2);
+          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].y, sy, ey, faccy, want_y2);
         }
       } else {
         // ynew = yn + sum_j hb_j F_j, err = sum_j hd_j F_j with F_{NV-1} = (du, dv): the operation order of finish_elem
@@ -590,14 +591,14 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
           const double2 f = (j == NV - 1) ? make_double2(du, dv) : pv[j + 1 < NV ? j + 1 : 0];
-          const bool nz = (fz.hb_nz >> j) & 1u;
+          const bool nz = (j < NV - 1) || nz_last;   // the stored stages' weights are non-zero (checked on the host)
           sx = fin_sol_term<EXACT>(fz.hb[j], f.x, sx, nz); ex = fin_err_term<EXACT>(fz.hd[j], f.x, ex);
           sy = fin_sol_term<EXACT>(fz.hb[j], f.y, sy, nz); ey = fin_err_term<EXACT>(fz.hd[j], f.y, ey);
         }
         if (active) {
           *out = make_double2(sx, sy);
           finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].x, sx, ex, facc, want_y2);
-          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].y, sy, ey, facc, want_y2);
+          finish_tail<EXACT>(fz.rtol, fz.atol, pv[0].y, sy, ey, faccy, want_y2);
         }
       }
       out += nx;
@@ -616,9 +617,9 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
 #pragma unroll
           for (int j = 0; j < NV - 1; ++j) {
             const double2 f = lds_f64x2(sa + (unsigned)((j + 1) * PITCH * 16));
-            const bool nz = (fz.hb_nz >> j) & 1u;
-            psum.x = fin_sol_term<EXACT>(fz.hb[j], f.x, psum.x, nz); perr.x = fin_err_term<EXACT>(fz.hd[j], f.x, perr.x);
-            psum.y = fin_sol_term<EXACT>(fz.hb[j], f.y, psum.y, nz); perr.y = fin_err_term<EXACT>(fz.hd[j], f.y, perr.y);
+            // (the stored stages' weights are non-zero: checked on the host before the launch)
+            psum.x = fin_sol_term<EXACT>(fz.hb[j], f.x, psum.x, true); perr.x = fin_err_term<EXACT>(fz.hd[j], f.x, perr.x);
+            psum.y = fin_sol_term<EXACT>(fz.hb[j], f.y, psum.y, true); perr.y = fin_err_term<EXACT>(fz.hd[j], f.y, perr.y);
           }
         }
       }
@@ -657,7 +658,8 @@ __global__ void __launch_bounds__(288, MINB) rhs_stream_kernel(const RhsArgs a, 
     // per-CTA sums in a fixed order: shuffle tree, then the eight consumer warps in order (the producer warp has left:
     // named barrier over the 256 consumer threads); the error sum travels as a double-double pair
     __shared__ double fin_red[3][8];
-    double eh = facc.e_hi, el = facc.e_lo, fy2 = facc.y2;
+    dd_merge(facc.e_hi, facc.e_lo, faccy.e_hi, faccy.e_lo);
+    double eh = facc.e_hi, el = facc.e_lo, fy2 = facc.y2 + faccy.y2;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { dd_shfl_down(eh, el, o); fy2 += __shfl_down_sync(0xffffffffu, fy2, o); }
     if (lane == 0) { fin_red[0][warp] = eh; fin_red[1][warp] = fy2; fin_red[2][warp] = el; }
