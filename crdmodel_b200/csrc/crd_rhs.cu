@@ -10,6 +10,8 @@
 //   crd_grid_create        geometry exactly as main() derives it, host-libm coefficient tables, ghost block
 //   crd_grid_halo_*        export / open the neighbours' ghost blocks (CUDA IPC or same-process peers)
 //   crd_rhs*, crd_f*       post the boundary rows, wait, launch (single slab / ring / overlapped ring / host buffers)
+#include <cstdlib>
+
 #include "crd_rhs_kernels.cuh"
 #include "crd_tables.hpp"
 
@@ -369,8 +371,10 @@ int crd_rhs_host(crd_grid *g, double t, const double *y_host, double *ydot_host)
     CRD_CUDA(cudaMalloc(&g->stage_ydot, row_bytes * nyl));
     CRD_CUDA(cudaStreamCreateWithFlags(&g->s_in, cudaStreamNonBlocking));
     CRD_CUDA(cudaStreamCreateWithFlags(&g->s_out, cudaStreamNonBlocking));
-    // chunks of ~64 MiB, at least 1 row, at most 64 chunks
-    long long rows_per = (long long)((64ull << 20) / row_bytes);
+    // chunks of ~64 MiB (CRD_HOST_CHUNK_MB), at least 1 row, at most 64 chunks
+    unsigned long long chunk_mb = 64;
+    if (const char *e = std::getenv("CRD_HOST_CHUNK_MB")) { const long v = std::atol(e); if (v > 0) chunk_mb = (unsigned long long)v; }
+    long long rows_per = (long long)((chunk_mb << 20) / row_bytes);
     if (rows_per < 1) rows_per = 1;
     long long n = (nyl + rows_per - 1) / rows_per;
     if (n > 64) n = 64;

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) gather_vars_kernel(const double2 *__restr
 
 struct crd_snapshot {
   crd_ctx *ctx = nullptr;
-  long long n = 0;
+  long long n = 0, stride = 0;    // stride: n rounded up to even (the second variable's array stays 16-byte aligned)
   int nvars = 1, nslots = 2;
   double *dev[kMaxSlots] = {};    // [nvars][n]
   double *host[kMaxSlots] = {};   // page-locked, same layout
@@ -50,7 +50,8 @@ crd_snapshot *crd_snapshot_create(crd_ctx *ctx, int64_t npoints, int nvars, int 
   if (use(ctx)) return nullptr;
   crd_snapshot *s = new crd_snapshot;
   s->ctx = ctx; s->n = npoints; s->nvars = nvars; s->nslots = nslots;
-  const size_t bytes = sizeof(double) * (size_t)npoints * (size_t)nvars;
+  s->stride = (npoints + 1) & ~1LL;
+  const size_t bytes = sizeof(double) * (size_t)s->stride * (size_t)nvars;
   cudaError_t e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
   for (int k = 0; k < nslots && e == cudaSuccess; ++k) {
     if ((e = cudaMalloc(&s->dev[k], bytes)) != cudaSuccess) break;
@@ -98,11 +99,11 @@ int crd_snapshot_begin(crd_snapshot *s, const double *y_dev) {
   if (blocks > (long long)c->sms * 16) blocks = (long long)c->sms * 16;
   if (blocks < 1) blocks = 1;
   gather_vars_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(reinterpret_cast<const double2 *>(y_dev), s->dev[k],
-                                                              s->nvars == 2 ? s->dev[k] + s->n : nullptr, s->n);
+                                                              s->nvars == 2 ? s->dev[k] + s->stride : nullptr, s->n);
   if (check_launch(c, "gather_vars_kernel")) return -1;
   CRD_CUDA(cudaEventRecord(s->gathered[k], c->stream));
   CRD_CUDA(cudaStreamWaitEvent(s->side, s->gathered[k], 0));
-  CRD_CUDA(cudaMemcpyAsync(s->host[k], s->dev[k], sizeof(double) * (size_t)s->n * (size_t)s->nvars, cudaMemcpyDeviceToHost, s->side));
+  CRD_CUDA(cudaMemcpyAsync(s->host[k], s->dev[k], sizeof(double) * (size_t)s->stride * (size_t)s->nvars, cudaMemcpyDeviceToHost, s->side));
   CRD_CUDA(cudaEventRecord(s->copied[k], s->side));
   s->busy[k] = true;
   s->used[k] = true;
@@ -116,7 +117,7 @@ int crd_snapshot_wait(crd_snapshot *s, int slot, const double **var0, const doub
   CRD_CUDA(cudaEventSynchronize(s->copied[slot]));
   if (device_failed(s->ctx)) return -1;
   if (var0) *var0 = s->host[slot];
-  if (var1) *var1 = s->nvars == 2 ? s->host[slot] + s->n : nullptr;
+  if (var1) *var1 = s->nvars == 2 ? s->host[slot] + s->stride : nullptr;
   return 0;
 }
 
