@@ -595,7 +595,8 @@ def main():
         return {"steps_per_s": (n1["nst"] - n0["nst"]) / dt_n, "step_attempts_per_s": att / dt_n, "ms_per_attempt": 1e3 * dt_n / att,
                 "nst": n1["nst"] - n0["nst"], "nfe": n1["nfe"] - n0["nfe"], "netf": n1["netf"] - n0["netf"],
                 "rhs_per_attempt": (n1["nfe"] - n0["nfe"]) / att, "flag": flag_n, "mode": "ARK_NORMAL, 50-step limit (flag -1 = the limit, as intended)",
-                "bytes_per_point_per_attempt": 384, "floor_ms_at_measured_peak": 384 * points / (peaks["hbm_gbs"] * 1e6),
+                "bytes_per_point_per_attempt": 272, "floor_ms_at_measured_peak": 272 * points / (peaks["hbm_gbs"] * 1e6),
+                "bytes_note": "3 x (2 vectors read + 1 written) + (5 read + 1 written) + f(tn, ynew) (1 read + 1 written), 16 B per point and vector",
                 "one_step_mode": {"steps_per_s": (n2["nst"] - n1["nst"]) / dt_1, "nst": n2["nst"] - n1["nst"], "flag": flag,
                                   "note": "ARK_ONE_STEP returns the state in the caller's vector: one more 32 B/point copy per call"},
                 "arith": label}
