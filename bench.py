@@ -682,6 +682,41 @@ def main():
             y5.destroy(); d5.destroy(); g5.close()
         except Exception as e:
             cfg5 = {"error": str(e)[:200]}
+    # ---- strong scaling of the literal BASELINE configs[3] mesh (16384 x 16384 in total, 1/N of its rows per GPU), N > 1 ----
+    strong = None
+    if extras and world > 1 and args.workload == "cfg4" and not args.strong:
+        try:
+            gs, jss, jes = make_grid("fhn_torus", NX, ROWS_PER_GPU)
+            ys, ds = gs.new_vector(), gs.new_vector()
+            gs.fill_synthetic(ys)
+            for _ in range(max(args.warmup, 10)):
+                gs.f(T_EVAL, ys, ds)
+            ctx.sync(); barrier()
+            ks = max(args.steps, 200)
+            mss = max_over_ranks(time_rhs(gs, ctx, ys, ds, ks))
+            barrier()
+            nss = int(min(100000, 2200.0 / max(mss / ks, 1e-3)))
+            msss = max_over_ranks(time_rhs(gs, ctx, ys, ds, nss))
+            barrier()
+            try:
+                pars = merge_parity(parity_rows(crd, ctx, gs, ys, ds, "fhn_torus", NX, ROWS_PER_GPU, jss, jes, args.arith, rank, n_interior=4))
+            except Exception as e:
+                pars = {"ok": False, "error": str(e)[:160]}
+                if use_dist:
+                    for op in ("sum", "min", "min", "max"):
+                        reduce_ranks(0.0, op)
+            ptss = NX * ROWS_PER_GPU
+            strong = {"what": "the literal BASELINE configs[3] mesh, theta 16384 x phi 16384 in total, %d rows per GPU" % (jes - jss + 1),
+                      "value": ptss * ks / (mss * 1e-3), "unit": UNIT, "steps": ks, "ms_per_step": mss / ks,
+                      "one_gpu_equivalent_ms": world * mss / ks,
+                      "frac_of_hbm_peak_per_gpu": BYTES_PER_POINT * ptss / world * ks / (mss * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                      "sustained": {"steps": nss, "seconds": msss * 1e-3, "ms_per_step": msss / nss,
+                                    "frac_of_hbm_peak_per_gpu": BYTES_PER_POINT * ptss / world * nss / (msss * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                      "parity": pars,
+                      "note": "compare one_gpu_equivalent_ms with ms_per_step of the N = 1 line (same steps count there: --steps)"}
+            ys.destroy(); ds.destroy(); gs.close()
+        except Exception as e:
+            strong = {"error": str(e)[:200]}
     if sampler:
         sampler.stop()
 
@@ -705,7 +740,7 @@ def main():
                 "parity": parity, "sustained": sustained, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks, "integrator": integ, "integrator_fast": integ_fast,
                 "integrator_stage_kernels": stage_kernels,
-                "integrator_default_meshes": integ_small, "cfg5": cfg5}
+                "integrator_default_meshes": integ_small, "cfg5": cfg5, "strong": strong}
         if world == 1 and extras and not args.no_cpu_baseline:
             try:
                 os.sched_setaffinity(0, all_cpus)

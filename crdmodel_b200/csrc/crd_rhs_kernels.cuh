@@ -759,12 +759,16 @@ int launch_stage_finish(crd_grid *g, const RhsArgs &a, const StageFin &fin, cuda
 #else
 #define CRD_FIN(M) CRD_FIN_(M, 2, 3)
 #endif
+  // Goldbeter in EXACT arithmetic is bound by FP64 work and issue slots, not by bytes in flight: 2 CTAs per SM with the
+  // registers that gives (no spills) are 6-8 % ahead of 3 (tools/prof_fin.py: 1.32-1.39 vs 1.44-1.48 ms at 8192 x 8192)
+#define CRD_FIN_GB(M) ((exact && g->variant == 0) ? launch_stream_nv<M, true, 5, false, 2, 2>(g, a, st, &fin, nblocks) : CRD_FIN(M))
   switch (g->p.model) {
     case CRD_FHN_TORUS: return CRD_FIN(CRD_FHN_TORUS);
-    case CRD_GOLDBETER_TORUS: return CRD_FIN(CRD_GOLDBETER_TORUS);
+    case CRD_GOLDBETER_TORUS: return CRD_FIN_GB(CRD_GOLDBETER_TORUS);
     case CRD_FHN_FLAT: return CRD_FIN(CRD_FHN_FLAT);
-    case CRD_GOLDBETER_FLAT: return CRD_FIN(CRD_GOLDBETER_FLAT);
+    case CRD_GOLDBETER_FLAT: return CRD_FIN_GB(CRD_GOLDBETER_FLAT);
   }
+#undef CRD_FIN_GB
 #undef CRD_FIN
 #undef CRD_FIN_
   return 1;
