@@ -96,8 +96,9 @@ namespace crd {
 inline int device_failed(crd_ctx *c) {
   if (!c->failed && c->err_host && *c->err_host != 0) {
     c->failed = true;
-    set_error("device-side error %d: the neighbour's halo rows did not arrive within %.1f s (rank %d of %d); the context is unusable",
-              *c->err_host, (double)c->halo_timeout_ns * 1e-9, c->rank, c->nranks);
+    set_error("device-side error %d: %s did not arrive within %.1f s (rank %d of %d); the context is unusable", *c->err_host,
+              *c->err_host == 110 ? "another rank's contribution to a reduction" : "a neighbour's halo rows",
+              (double)c->halo_timeout_ns * 1e-9, c->rank, c->nranks);
     return 1;
   }
   return c->failed ? 1 : 0;

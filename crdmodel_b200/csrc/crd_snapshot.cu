@@ -7,6 +7,8 @@
 //   side stream         : [wait: gather done] cudaMemcpyAsync device -> page-locked host buffer of the slot, event
 // and the time loop continues at once; the formatter thread (host/crd_writer.hpp) waits for the slot's event.  Only the
 // variables that are written travel over PCIe (8 B/point instead of 16 when includeAllVars = 0).
+#include <atomic>
+
 #include "crd_common.cuh"
 
 using namespace crd;
@@ -37,7 +39,7 @@ struct crd_snapshot {
   double *dev[kMaxSlots] = {};    // [nvars][n]
   double *host[kMaxSlots] = {};   // page-locked, same layout
   cudaEvent_t gathered[kMaxSlots] = {}, copied[kMaxSlots] = {};
-  bool busy[kMaxSlots] = {};      // handed out by begin, not yet released
+  std::atomic<bool> busy[kMaxSlots];   // handed out by begin (the context's thread), released by the consumer thread
   bool used[kMaxSlots] = {};
   cudaStream_t side = nullptr;
   int next = 0;
@@ -49,6 +51,7 @@ crd_snapshot *crd_snapshot_create(crd_ctx *ctx, int64_t npoints, int nvars, int 
   if (!ctx || npoints < 1 || nvars < 1 || nvars > 2 || nslots < 1 || nslots > kMaxSlots) { set_error("crd_snapshot_create: bad arguments"); return nullptr; }
   if (use(ctx)) return nullptr;
   crd_snapshot *s = new crd_snapshot;
+  for (auto &b : s->busy) b.store(false);
   s->ctx = ctx; s->n = npoints; s->nvars = nvars; s->nslots = nslots;
   s->stride = (npoints + 1) & ~1LL;
   const size_t bytes = sizeof(double) * (size_t)s->stride * (size_t)nvars;
@@ -89,7 +92,7 @@ int crd_snapshot_begin(crd_snapshot *s, const double *y_dev) {
   int k = -1;
   for (int t = 0; t < s->nslots; ++t) {
     const int cand = (s->next + t) % s->nslots;
-    if (!s->busy[cand]) { k = cand; break; }
+    if (!s->busy[cand].load(std::memory_order_acquire)) { k = cand; break; }
   }
   if (k < 0) return -2;
   s->next = (k + 1) % s->nslots;
@@ -105,14 +108,14 @@ int crd_snapshot_begin(crd_snapshot *s, const double *y_dev) {
   CRD_CUDA(cudaStreamWaitEvent(s->side, s->gathered[k], 0));
   CRD_CUDA(cudaMemcpyAsync(s->host[k], s->dev[k], sizeof(double) * (size_t)s->stride * (size_t)s->nvars, cudaMemcpyDeviceToHost, s->side));
   CRD_CUDA(cudaEventRecord(s->copied[k], s->side));
-  s->busy[k] = true;
+  s->busy[k].store(true, std::memory_order_release);
   s->used[k] = true;
   return k;
 }
 
 // Block until the slot's values are on the host (any host thread); var0 / var1: contiguous [npoints] each (var1 NULL if not captured)
 int crd_snapshot_wait(crd_snapshot *s, int slot, const double **var0, const double **var1) {
-  if (!s || slot < 0 || slot >= s->nslots || !s->busy[slot]) { set_error("crd_snapshot_wait: bad slot"); return -1; }
+  if (!s || slot < 0 || slot >= s->nslots || !s->busy[slot].load(std::memory_order_acquire)) { set_error("crd_snapshot_wait: bad slot"); return -1; }
   CRD_CUDA(cudaSetDevice(s->ctx->device));
   CRD_CUDA(cudaEventSynchronize(s->copied[slot]));
   if (device_failed(s->ctx)) return -1;
@@ -123,7 +126,7 @@ int crd_snapshot_wait(crd_snapshot *s, int slot, const double **var0, const doub
 
 int crd_snapshot_release(crd_snapshot *s, int slot) {
   if (!s || slot < 0 || slot >= s->nslots) return -1;
-  s->busy[slot] = false;
+  s->busy[slot].store(false, std::memory_order_release);
   return 0;
 }
 
