@@ -352,9 +352,10 @@ def stage_kernel_times(crd, ctx, grid, y, ydot, model, nx, nyl, reps=20):
             v.destroy()
 
 
-def copy_ceiling(torch, nbytes, reps=2):
+def copy_ceiling(torch, nbytes, reps=3):
     """What the PCIe / host-memory path allows with no kernel in between: one H2D and one D2H cudaMemcpyAsync of `nbytes` each,
-    from / into page-locked host memory, in flight together on two streams (the traffic of one e2e step)."""
+    from / into page-locked host memory, in flight together on two streams (the traffic of one e2e step).  Timed like the e2e
+    leg: one warm-up, then the MEAN over `reps` back-to-back repetitions (the caller takes the max over ranks)."""
     n = nbytes // 8
     h_in = torch.empty(n, dtype=torch.float64, pin_memory=True)
     h_out = torch.empty(n, dtype=torch.float64, pin_memory=True)
@@ -362,19 +363,20 @@ def copy_ceiling(torch, nbytes, reps=2):
     d_out = torch.zeros(n, dtype=torch.float64, device="cuda")
     h_in.zero_()
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-    best = None
-    for _ in range(reps + 1):
-        torch.cuda.synchronize()
-        t0 = time.time()
+
+    def once():
         with torch.cuda.stream(s1):
             d_in.copy_(h_in, non_blocking=True)
         with torch.cuda.stream(s2):
             h_out.copy_(d_out, non_blocking=True)
         torch.cuda.synchronize()
-        dt = time.time() - t0
-        best = dt if best is None else min(best, dt)
+    once()
+    t0 = time.time()
+    for _ in range(reps):
+        once()
+    dt = (time.time() - t0) / reps
     del h_in, h_out, d_in, d_out
-    return best
+    return dt
 
 
 def time_rhs(grid, ctx, y, ydot, steps):
@@ -554,9 +556,10 @@ def main():
     ceiling = None
     try:
         barrier()
-        c_s = max_over_ranks(copy_ceiling(torch, nbytes))
+        c_s = max_over_ranks(copy_ceiling(torch, nbytes, max(1, args.e2e_steps)))
         ceiling = {"ms_per_step": 1e3 * c_s, "GBs_each_way_per_gpu": nbytes / c_s / 1e9,
-                   "what": "one cudaMemcpyAsync H2D + one D2H of the step's bytes from / to page-locked memory, concurrently, on all %d rank(s) at once" % world}
+                   "what": "one cudaMemcpyAsync H2D + one D2H of the step's bytes from / to page-locked memory, concurrently, on all %d rank(s) at once; "
+                           "mean over %d repetitions after a warm-up, max over ranks (timed like the e2e leg)" % (world, max(1, args.e2e_steps))}
     except Exception as e:
         ceiling = {"error": str(e)[:160]}
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
