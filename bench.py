@@ -379,6 +379,36 @@ def copy_ceiling(torch, nbytes, reps=3):
     return dt
 
 
+def integrator_fingerprint(crd, ctx, g, y, world, gloo_group, steps=5):
+    """A few steps of the fused EXACT integrator from the synthetic state on the 16384 x 16384 mesh (one slab at N = 1, split
+    over the GPUs at N > 1), then a fingerprint of the state that does not depend on the partition: the sum (mod 2^64) and the
+    XOR of all elements' bit patterns, with the step counters and the time reached.  EXACT arithmetic makes the integration
+    independent of the split bit for bit, so this dictionary must be the same at every N."""
+    import numpy as np
+    g.fill_synthetic(y)
+    solver = crd.ARKodeSolver(g, y, t0=T_EVAL, fused="full", max_steps=steps)
+    solver.set_init_step(1e-9)
+    flag, t = solver.ARKode(T_EVAL + 1.0, crd.ARK_NORMAL)          # stops at the step limit (flag -1) with the state in y
+    st = solver.stats()
+    solver.free()
+    bits = y.to_numpy().view(np.uint64)
+    part = (int(np.add.reduce(bits, dtype=np.uint64)), int(np.bitwise_xor.reduce(bits)))
+    del bits
+    parts = [part]
+    if world > 1:
+        import torch.distributed as dist
+        parts = [None] * world
+        dist.all_gather_object(parts, part, group=gloo_group)
+    ssum, sxor = 0, 0
+    for a, b in parts:
+        ssum = (ssum + a) & 0xFFFFFFFFFFFFFFFF
+        sxor ^= b
+    g.fill_synthetic(y)
+    return {"mesh": "theta 16384 x phi 16384 in total", "steps": st["nst"], "netf": st["netf"], "nfe": st["nfe"], "t": float(t).hex(), "flag": flag,
+            "sum64": "%016x" % ssum, "xor64": "%016x" % sxor,
+            "note": "same dictionary at every N = the phi split does not change a bit of the integration"}
+
+
 def time_rhs(grid, ctx, y, ydot, steps):
     ctx.timer_start()
     for _ in range(steps):
@@ -627,6 +657,13 @@ def main():
             except Exception as e:
                 integ_fast = {"error": str(e)[:200]}
 
+    fingerprint = None
+    if extras and not args.no_integrator and world == 1 and args.workload == "cfg4" and args.arith == "exact" and nx == NX and nyl == ROWS_PER_GPU:
+        try:
+            fingerprint = integrator_fingerprint(crd, ctx, grid, y, 1, None)
+        except Exception as e:
+            fingerprint = {"error": str(e)[:200]}
+
     # ---- the reference's own default meshes (BASELINE configs[1], [2]): whole adaptive integrations ----
     integ_small = None
     if extras and not args.no_integrator and world == 1:
@@ -708,6 +745,11 @@ def main():
                 if use_dist:
                     for op in ("sum", "min", "min", "max"):
                         reduce_ranks(0.0, op)
+            if not args.no_integrator and args.arith == "exact":
+                try:
+                    fingerprint = integrator_fingerprint(crd, ctx, gs, ys, world, gloo)
+                except Exception as e:
+                    fingerprint = {"error": str(e)[:200]}
             ptss = NX * ROWS_PER_GPU
             strong = {"what": "the literal BASELINE configs[3] mesh, theta 16384 x phi 16384 in total, %d rows per GPU" % (jes - jss + 1),
                       "value": ptss * ks / (mss * 1e-3), "unit": UNIT, "steps": ks, "ms_per_step": mss / ks,
@@ -743,7 +785,7 @@ def main():
                 "parity": parity, "sustained": sustained, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks, "integrator": integ, "integrator_fast": integ_fast,
                 "integrator_stage_kernels": stage_kernels,
-                "integrator_default_meshes": integ_small, "cfg5": cfg5, "strong": strong}
+                "integrator_default_meshes": integ_small, "cfg5": cfg5, "strong": strong, "integrator_fingerprint": fingerprint}
         if world == 1 and extras and not args.no_cpu_baseline:
             try:
                 os.sched_setaffinity(0, all_cpus)
