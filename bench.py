@@ -182,10 +182,14 @@ def parity_rows(crd, ctx, grid, y, ydot, model, nx, ny, js, je, arith, rank, tim
     bands = [(js, 2), (je - 1, 2)] + [(int(j), 2) for j in rng.integers(js + 2, je - 2, n_interior)]
     bitwise, worst, rows = True, 0.0, 0
     # tolerance when the kinetics go through libm pow (Goldbeter) or the arithmetic is FAST: relative to the summed |terms|
-    dx, dy = 2 * np.pi / (nx - 1), 2 * np.pi / (ny - 1)
-    r2, Rm = (20.0 / (2 * np.pi)) ** 2, 60.0 / (2 * np.pi)
-    scale = 0.12 * 5 * 2.0 * (4.0 / (r2 * dx * dx) + 4.0 / (Rm * Rm * dy * dy)) + 700.0 * 5.0
-    tol = 0.0 if (model == "fhn_torus" and arith == "exact") else (4e-16 if arith == "exact" else 1e-12) * scale
+    if model.endswith("torus"):
+        dx, dy = 2 * np.pi / (nx - 1), 2 * np.pi / (ny - 1)
+        r2, Rm = (20.0 / (2 * np.pi)) ** 2, 60.0 / (2 * np.pi)
+        scale = 0.12 * 5 * 2.0 * (4.0 / (r2 * dx * dx) + 4.0 / (Rm * Rm * dy * dy)) + 700.0 * 5.0
+    else:                                                   # flat: D (uW + uE)/dx^2 + D (uS + uN)/dy^2 - 2 D (1/dx^2 + 1/dy^2) u
+        dx, dy = 20.0 / (nx - 1), 80.0 / (ny - 1)
+        scale = 0.12 * 2.0 * 8.0 * (1.0 / (dx * dx) + 1.0 / (dy * dy)) + 700.0 * 5.0
+    tol = 0.0 if (model.startswith("fhn") and arith == "exact") else (4e-16 if arith == "exact" else 1e-12) * scale
     for t in times:
         grid.f(t, y, ydot)
         for j0, n in bands:
@@ -350,6 +354,76 @@ def stage_kernel_times(crd, ctx, grid, y, ydot, model, nx, nyl, reps=20):
     finally:
         for v in X[1:]:
             v.destroy()
+
+
+def nvector_op_times(crd, ctx, grid, y, ydot, peaks, reps=10):
+    """The N_Vector operations the explicit integrator calls (SUNDIALS 2.x table order) on vectors of the headline
+    mesh, each timed alone with CUDA events over `reps` back-to-back calls through the C ABI.  Algorithmic bytes per element: 8 per
+    vector read or written.  A reduction returns its value to the caller, so one stream synchronisation (and, for N > 1, the
+    exchange between the GPUs) per call is inside its time."""
+    z, w = grid.new_vector(), grid.new_vector()
+    try:
+        n = y.n
+        crd.N_VScale(0.5, y, w)
+        crd.N_VAbs(y, z); crd.N_VAddConst(z, 0.5, z)        # z > 0: a weight vector / a safe divisor
+        h = 1e-3
+        ops = [
+            ("N_VLinearSum", 3, lambda: crd.N_VLinearSum(1.5, y, -0.25, z, ydot)),
+            ("N_VLinearSum in place (z = a x + z)", 3, lambda: crd.N_VLinearSum(1e-9, y, 1.0, ydot, ydot)),
+            ("N_VConst", 1, lambda: crd.N_VConst(0.0, ydot)),
+            ("N_VProd", 3, lambda: crd.N_VProd(y, z, ydot)),
+            ("N_VDiv", 3, lambda: crd.N_VDiv(y, z, ydot)),
+            ("N_VScale", 2, lambda: crd.N_VScale(0.75, y, ydot)),
+            ("N_VAbs", 2, lambda: crd.N_VAbs(y, ydot)),
+            ("N_VInv", 2, lambda: crd.N_VInv(z, ydot)),
+            ("N_VAddConst", 2, lambda: crd.N_VAddConst(y, 1e-10, ydot)),
+            ("N_VDotProd", 2, lambda: crd.N_VDotProd(y, z)),
+            ("N_VMaxNorm", 1, lambda: crd.N_VMaxNorm(y)),
+            ("N_VWrmsNorm", 2, lambda: crd.N_VWrmsNorm(y, z)),
+            ("N_VMin", 1, lambda: crd.N_VMin(z)),
+            ("N_VWL2Norm", 2, lambda: crd.N_VWL2Norm(y, z)),
+            ("N_VL1Norm", 1, lambda: crd.N_VL1Norm(y)),
+            ("N_VLinearCombination (3 vectors, fused stage assembly)", 4, lambda: crd.N_VLinearCombination([1.0, 0.5 * h, 0.25 * h], [y, z, w], ydot)),
+        ]
+        out = []
+        for name, nvec, call in ops:
+            call(); call()
+            ctx.sync(); ctx.timer_start()
+            for _ in range(reps):
+                call()
+            ms = ctx.timer_stop() / reps
+            gbs = 8.0 * nvec * n / ms / 1e6
+            out.append({"op": name, "ms": ms, "bytes_per_element": 8 * nvec, "GBs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]})
+        return {"elements_per_gpu": n, "launches_timed_per_op": reps, "ops": out,
+                "note": "CUDA events around %d consecutive calls of each operation on the headline mesh's vectors (%.2f GB each)" % (reps, 8 * n / 1e9)}
+    finally:
+        z.destroy(); w.destroy()
+
+
+def flat_models_block(crd, ctx, peaks, arith, arith_name, steps, warmup):
+    """The two flat programs of the reference (BASELINE configs[0] is the FHN flat mesh on the CPU) on a mesh
+    beyond L2, one GPU: same timing as the headline, rows of the result against the reference's own f()."""
+    out = []
+    for model, nx, ny in (("fhn_flat", 16384, 8192), ("gb_flat", 8192, 8192)):
+        g = crd.Grid(ctx, crd.make_params(model, nx, ny, arith=arith))
+        y, d = g.new_vector(), g.new_vector()
+        try:
+            g.fill_synthetic(y)
+            for _ in range(max(warmup, 5)):
+                g.f(T_EVAL, y, d)
+            ctx.sync()
+            k = max(steps, 50)
+            ms = time_rhs(g, ctx, y, d, k)
+            row = {"model": model, "nx": nx, "ny": ny, "steps": k, "ms_per_step": ms / k, "value": nx * ny * k / (ms * 1e-3), "unit": UNIT,
+                   "frac_of_hbm_peak": BYTES_PER_POINT * nx * ny * k / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+            try:
+                row["parity"] = parity_rows(crd, ctx, g, y, d, model, nx, ny, 0, ny - 1, arith_name, 0, n_interior=4)
+            except Exception as e:
+                row["parity"] = {"ok": False, "error": "%s: %s" % (type(e).__name__, str(e)[:160])}
+            out.append(row)
+        finally:
+            y.destroy(); d.destroy(); g.close()
+    return out
 
 
 def copy_ceiling(torch, nbytes, reps=3):
@@ -683,7 +757,24 @@ def main():
         except Exception as e:
             stage_kernels = {"error": str(e)[:200]}
 
+    # ---- the N_Vector operations of the integrator, each timed alone on the headline mesh's vectors ----
+    nvec_ops = None
+    if extras and args.workload == "cfg4" and not args.strong:
+        try:
+            grid.fill_synthetic(y)
+            nvec_ops = nvector_op_times(crd, ctx, grid, y, ydot, peaks)
+        except Exception as e:
+            nvec_ops = {"error": str(e)[:200]}
+
     y.destroy(); ydot.destroy(); grid.close()
+
+    # ---- the reference's two flat programs (one GPU) ----
+    flat = None
+    if extras and world == 1 and args.workload == "cfg4":
+        try:
+            flat = flat_models_block(crd, ctx, peaks, arith, args.arith, args.steps, args.warmup)
+        except Exception as e:
+            flat = {"error": str(e)[:200]}
 
     # ---- BASELINE configs[4] beside the headline, at every N: Goldbeter torus theta 8192 x 4096 phi rows per GPU --------
     cfg5 = None
@@ -785,7 +876,8 @@ def main():
                 "parity": parity, "sustained": sustained, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks, "integrator": integ, "integrator_fast": integ_fast,
                 "integrator_stage_kernels": stage_kernels,
-                "integrator_default_meshes": integ_small, "cfg5": cfg5, "strong": strong, "integrator_fingerprint": fingerprint}
+                "integrator_default_meshes": integ_small, "cfg5": cfg5, "strong": strong, "integrator_fingerprint": fingerprint,
+                "nvector_ops": nvec_ops, "flat_models": flat}
         if world == 1 and extras and not args.no_cpu_baseline:
             try:
                 os.sched_setaffinity(0, all_cpus)

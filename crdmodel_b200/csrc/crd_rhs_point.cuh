@@ -153,8 +153,9 @@ __device__ __forceinline__ void react(const RhsConst &k, double b, double u, dou
       const double v2 = __ddiv_rn(__dmul_rn(G_VM2, z2), __dadd_rn(k.k2n, z2));
       const double v3 = __ddiv_rn(__dmul_rn(__dmul_rn(G_VM3, y2), z4),
                                   __dmul_rn(__dadd_rn(k.krm, y2), __dadd_rn(k.kap, z4)));
-      du = __dadd_rn(du, __dsub_rn(__dadd_rn(__dadd_rn(__dsub_rn(b, v2), v3), __dmul_rn(G_kf, Y)), __dmul_rn(G_k, Z)));
-      dv = __dsub_rn(__dsub_rn(v2, v3), __dmul_rn(G_kf, Y));   // never -0 (v2 - v3 is +0 when it vanishes), so 0.0 + dv == dv
+      const double kfY = (G_kf == 1.0) ? Y : __dmul_rn(G_kf, Y);   // 1.0 * Y is Y, bit for bit
+      du = __dadd_rn(du, __dsub_rn(__dadd_rn(__dadd_rn(__dsub_rn(b, v2), v3), kfY), __dmul_rn(G_k, Z)));
+      dv = __dsub_rn(__dsub_rn(v2, v3), kfY);   // never -0 (v2 - v3 is +0 when it vanishes), so 0.0 + dv == dv
     } else {
       // w = v2 - v3 = A/B - C/D with one reciprocal: (A*D - C*B) / (B*D)
       const double z2 = Z * Z, y2 = Y * Y, z4 = z2 * z2;
