@@ -84,42 +84,48 @@ crd_ctx *crd_ctx_create(int device, void *stream) {
     const long long ms = std::atoll(e);
     if (ms > 0) c->halo_timeout_ns = ms * 1000000LL;
   }
-  if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
-  else { CRD_CUDA_NULL(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-  CRD_CUDA_NULL(cudaMalloc(&c->red_partial, sizeof(double) * kRedSlots * kRedBlocks));
-  CRD_CUDA_NULL(cudaMalloc(&c->red_ticket, sizeof(unsigned int)));
-  CRD_CUDA_NULL(cudaMemset(c->red_ticket, 0, sizeof(unsigned int)));
-  CRD_CUDA_NULL(cudaHostAlloc(&c->red_result_host, sizeof(double) * kRedSlots, cudaHostAllocMapped));
-  CRD_CUDA_NULL(cudaHostGetDevicePointer(&c->red_result_dev, c->red_result_host, 0));
-  CRD_CUDA_NULL(cudaMalloc(&c->red_local, sizeof(double) * kRedSlots));
-  CRD_CUDA_NULL(cudaMalloc(&c->comm_local, kCommBlockBytes));
-  CRD_CUDA_NULL(cudaMemset(c->comm_local, 0, kCommBlockBytes));
-  CRD_CUDA_NULL(cudaMalloc(&c->comm_tab, sizeof(CommTab)));
-  CRD_CUDA_NULL(cudaHostAlloc(&c->err_host, sizeof(int), cudaHostAllocMapped));
-  *c->err_host = 0;
-  CRD_CUDA_NULL(cudaHostGetDevicePointer(&c->err_dev, c->err_host, 0));
-  CRD_CUDA_NULL(cudaEventCreate(&c->ev0));
-  CRD_CUDA_NULL(cudaEventCreate(&c->ev1));
+  // every allocation below is released by crd_ctx_destroy, which tolerates the ones that never happened
+  auto setup = [&]() -> int {
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else { CRD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    CRD_CUDA(cudaMalloc(&c->red_partial, sizeof(double) * kRedSlots * kRedBlocks));
+    CRD_CUDA(cudaMalloc(&c->red_ticket, sizeof(unsigned int)));
+    CRD_CUDA(cudaMemset(c->red_ticket, 0, sizeof(unsigned int)));
+    CRD_CUDA(cudaHostAlloc(&c->red_result_host, sizeof(double) * kRedSlots, cudaHostAllocMapped));
+    CRD_CUDA(cudaHostGetDevicePointer(&c->red_result_dev, c->red_result_host, 0));
+    CRD_CUDA(cudaMalloc(&c->red_local, sizeof(double) * kRedSlots));
+    CRD_CUDA(cudaMalloc(&c->comm_local, kCommBlockBytes));
+    CRD_CUDA(cudaMemset(c->comm_local, 0, kCommBlockBytes));
+    CRD_CUDA(cudaMalloc(&c->comm_tab, sizeof(CommTab)));
+    CRD_CUDA(cudaHostAlloc(&c->err_host, sizeof(int), cudaHostAllocMapped));
+    *c->err_host = 0;
+    CRD_CUDA(cudaHostGetDevicePointer(&c->err_dev, c->err_host, 0));
+    CRD_CUDA(cudaEventCreate(&c->ev0));
+    CRD_CUDA(cudaEventCreate(&c->ev1));
+    return 0;
+  };
+  if (setup() != 0) { crd_ctx_destroy(c); return nullptr; }
   return c;
 }
 
 void crd_ctx_destroy(crd_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  if (c->own_stream) cudaStreamDestroy(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   for (int r = 0; r < kMaxRanks; ++r)
     if (c->comm_peer[r]) cudaIpcCloseMemHandle(c->comm_peer[r]);
-  cudaFree(c->comm_local);
-  cudaFree(c->comm_tab);
-  cudaFree(c->red_local);
-  cudaFree(c->red_partial);
-  cudaFree(c->red_ticket);
-  cudaFreeHost(c->red_result_host);
-  cudaFreeHost(c->err_host);
+  if (c->comm_local) cudaFree(c->comm_local);
+  if (c->comm_tab) cudaFree(c->comm_tab);
+  if (c->red_local) cudaFree(c->red_local);
+  if (c->red_partial) cudaFree(c->red_partial);
+  if (c->red_ticket) cudaFree(c->red_ticket);
+  if (c->red_result_host) cudaFreeHost(c->red_result_host);
+  if (c->err_host) cudaFreeHost(c->err_host);
   if (c->flush_buf) cudaFree(c->flush_buf);
-  cudaEventDestroy(c->ev0);
-  cudaEventDestroy(c->ev1);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  cudaGetLastError();
   delete c;
 }
 
@@ -171,6 +177,9 @@ int crd_ctx_comm_connect_ipc(crd_ctx *c, int rank, int nranks, const unsigned ch
   if (!c || !handles || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) { set_error("crd_ctx_comm_connect_ipc: bad arguments"); return -1; }
   if (use(c)) return -1;
   char *blocks[kMaxRanks];
+  for (int r = 0; r < kMaxRanks; ++r)      // connecting again replaces the earlier mappings
+    if (c->comm_peer[r]) { cudaIpcCloseMemHandle(c->comm_peer[r]); c->comm_peer[r] = nullptr; }
+  c->dev_comm = false;
   for (int r = 0; r < nranks; ++r) {
     if (r == rank) { blocks[r] = c->comm_local; continue; }
     cudaIpcMemHandle_t h;

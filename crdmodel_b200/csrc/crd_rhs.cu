@@ -107,9 +107,22 @@ int crd_grid_halo_connect_ipc(crd_grid *g, const unsigned char prev_handle[CRD_H
   std::memcpy(&hp, prev_handle, sizeof hp);
   std::memcpy(&hn, next_handle, sizeof hn);
   void *pp = nullptr, *pn = nullptr;
+  if (g->connected) {   // connecting again replaces the earlier mappings
+    if (g->prev_ipc && g->halo_prev) cudaIpcCloseMemHandle(g->halo_prev);
+    if (g->next_ipc && g->halo_next && g->halo_next != g->halo_prev) cudaIpcCloseMemHandle(g->halo_next);
+    g->halo_prev = g->halo_next = nullptr;
+    g->prev_ipc = g->next_ipc = g->connected = false;
+  }
   CRD_CUDA(cudaIpcOpenMemHandle(&pp, hp, cudaIpcMemLazyEnablePeerAccess));
   if (std::memcmp(&hp, &hn, sizeof hp) == 0) pn = pp;  // two ranks: both neighbours are the same block
-  else CRD_CUDA(cudaIpcOpenMemHandle(&pn, hn, cudaIpcMemLazyEnablePeerAccess));
+  else {
+    cudaError_t e = cudaIpcOpenMemHandle(&pn, hn, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaIpcCloseMemHandle(pp);
+      set_error("crd_grid_halo_connect_ipc: cudaIpcOpenMemHandle -> %s", cudaGetErrorString(e));
+      return -1;
+    }
+  }
   g->halo_prev = (char *)pp; g->halo_next = (char *)pn;
   g->prev_ipc = g->next_ipc = true;
   g->connected = true;
