@@ -288,7 +288,7 @@ class Grid:
         check(lib().crd_grid_set_variant(self._h, v), "crd_grid_set_variant")
 
     def set_resident(self, mode):
-        """Device-resident step loop: 0 automatic (meshes of up to 4 Mi points), 1 whenever it applies, -1 never."""
+        """Device-resident step loop: 0 automatic (meshes of up to 1 Mi points), 1 whenever it applies, -1 never."""
         check(lib().crd_grid_set_resident(self._h, mode), "crd_grid_set_resident")
 
     @property

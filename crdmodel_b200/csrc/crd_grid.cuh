@@ -92,6 +92,30 @@ struct HaloLayout {
   __host__ __device__ size_t bytes() const { return flag_off(2); }
 };
 
+// Rows per segment of the streaming kernel.  Its units (256-column strips x row segments) go to the persistent CTAs round-robin,
+// so a launch lasts ceil(units / ctas) unit times: pick the segment length that fills whole waves — a unit costs its rows plus
+// the two rows above and below it that are fetched on top (and about one row of start-up).  Keeps every CTA busy on meshes of a
+// few million points (1024 x 4096 with fixed 128-row segments: 128 units for 444 CTAs) and trims the last partial wave of large ones.
+inline int stream_seg_rows(long long nyl, long long strips, long long ctas) {
+  int best = 0;
+  long long best_cost = 0;
+  for (long long w = 1; w <= 256; ++w) {
+    long long nseg = ctas * w / strips;
+    if (nseg < 1) continue;
+    if (nseg > nyl) nseg = nyl;
+    const long long rows = (nyl + nseg - 1) / nseg;
+    if (rows < 16) break;            // more waves only shorten the segments further
+    if (rows > 512) continue;
+    nseg = (nyl + rows - 1) / rows;
+    const long long waves = (strips * nseg + ctas - 1) / ctas;
+    const long long cost = waves * (rows + 3);
+    if (best == 0 || cost < best_cost) { best = (int)rows; best_cost = cost; }
+  }
+  if (best == 0) best = nyl < 16 ? (int)(nyl > 0 ? nyl : 1) : 16;
+  return best;
+}
+
+
 }  // namespace crd
 
 struct crd_grid {

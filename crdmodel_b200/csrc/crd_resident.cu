@@ -566,9 +566,10 @@ ResKernel *res_pick(int model, bool exact, int ticks) {
   return nullptr;
 }
 
-// meshes up to this many points run the resident loop by default: beyond it a pass is HBM-bound and the TMA-tiled
-// kernels of the launch-per-stage path are the faster way to stream it
-constexpr long long kResidentAutoPoints = 4LL << 20;
+// meshes up to this many points run the resident loop by default: its working set (8 storages of 16 B per point) then lives in
+// shared memory and the 126 MB L2; beyond it every pass between two grid barriers streams from HBM, which the launch-per-stage
+// kernels do faster (500 x 2000: 80 vs 122 us per step resident / launch-per-stage; 550 x 2200: 169 vs 117; profiles/README.md)
+constexpr long long kResidentAutoPoints = 1LL << 20;
 
 }  // namespace
 
@@ -660,6 +661,7 @@ int crd_erk_evolve(struct crd_erk_state *st, void *user_data) {
   if ((size_t)smem_optin < reserve + slot_bytes) return 1;   // not even the stage tile of a band fits: the launch-per-stage path streams this mesh
   int nslots = (int)(((size_t)smem_optin - reserve) / slot_bytes) - 1;
   if (nslots > ST_N) nslots = ST_N;
+
   if (g->variant >= 120 && g->variant <= 120 + ST_N && nslots > g->variant - 120) nslots = g->variant - 120;   // 120 + n: at most n storages in shared memory
   P.nslots = nslots;
   P.slot_bytes = (unsigned)slot_bytes;

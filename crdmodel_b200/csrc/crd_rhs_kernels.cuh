@@ -3,6 +3,7 @@
 // initial-condition kernel, and their launchers.  Included once, by crd_rhs.cu, which holds the C ABI.
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "crd_fused.cuh"
@@ -710,9 +711,12 @@ __global__ void __launch_bounds__(256) fin_reduce_kernel(const double *partial, 
 template <int MODEL, bool EXACT, int NV, bool PLAIN, int FIN = 0, int MINB = 2>
 int launch_stream_nv(crd_grid *g, const RhsArgs &a, cudaStream_t st, const StageFin *fin = nullptr, int *nblocks = nullptr) {
   constexpr int RB = (NV == 1) ? 4 : (NV <= 3 ? 2 : 1);   // rows per ring stage
-  const int seg_rows = 128;
-  const long long strips = (a.nx + 255) / 256, segs = (a.nyl + seg_rows - 1) / seg_rows, units = strips * segs;
-  if (units <= 0) return 0;
+  const long long strips = (a.nx + 255) / 256;
+  if (strips <= 0 || a.nyl <= 0) return 0;
+  int seg_rows = stream_seg_rows(a.nyl, strips, (long long)MINB * g->ctx->sms);
+  static const int seg_override = [] { const char *e = std::getenv("CRD_STREAM_SEG_ROWS"); return e ? std::atoi(e) : 0; }();   // profiling
+  if (seg_override >= 1) seg_rows = seg_override;
+  const long long segs = (a.nyl + seg_rows - 1) / seg_rows, units = strips * segs;
   const size_t stage_bytes = (size_t)RB * NV * 258 * 16;
   int S = (int)((MINB == 3 ? 68000 : 100000) / stage_bytes);
   if (S > 8) S = 8;
@@ -778,7 +782,7 @@ int launch_stage_finish(crd_grid *g, const RhsArgs &a, const StageFin &fin, cuda
 //   1..5 the direct kernel (rows per thread, min CTAs/SM): 1 (2,4) | 2 (8,2) | 3 (1,4) | 4 (4,3) | 5 (4,4)
 //   10, 13, 15 the tiled kernel (TX, TY, min CTAs/SM): 10 (128,16,4) | 13 (256,16,3) | 15 = 13 with flag-and-redo instead of a
 //              branch per point;   20, 21 the streaming kernel with 2 | 3 CTAs per SM.
-// Grid variant 0 = automatic.  Large slabs (>= 4 Mi points, HBM-bound): the TMA-tiled kernel wherever a tile row is reasonably
+// Grid variant 0 = automatic.  Large slabs (>= 2 Mi points, beyond L2 with their result): the TMA-tiled kernel wherever a tile row is reasonably
 // full; the streaming kernel for the fused stages (its once-per-row fetch beats the tiled kernel's register-staged tiles: 3
 // CTAs/SM for 2 or 3 input vectors, 2 for 5).  Small slabs (the reference's default 400 x 1600 / 100 x 400 grids live in L2 and
 // are bound by launch latency and by how many CTAs a partial wave gets): the direct kernel with 2 rows per thread.  Measured:
@@ -787,10 +791,11 @@ int launch_stage_finish(crd_grid *g, const RhsArgs &a, const StageFin &fin, cuda
 inline int resolved_variant(const crd_grid *g, long long nx, long long nyl, int nlc) {
   const bool exact = g->p.arith == CRD_ARITH_EXACT;
   int variant = g->variant;
-  const bool big = nx * nyl >= (4LL << 20);
+  const bool big = nx * nyl >= (2LL << 20), mid = nx * nyl >= (1LL << 20);
   if (variant == 0) {
-    if (!big) variant = 1;
-    else variant = (nx >= 192) ? ((exact && !is_fhn(g->p.model)) ? 15 : 13) : (nx >= 96) ? 10 : 5;
+    const int tiled = (exact && !is_fhn(g->p.model)) ? 15 : 13;
+    if (!big) variant = (mid && nlc > 0 && nx >= 192) ? tiled : 1;   // 1-2 Mi points: a fused stage is already faster tiled
+    else variant = (nx >= 192) ? tiled : (nx >= 96) ? 10 : 5;
     if (nlc == 5 && nx >= 192 && big) variant = 20;
     if ((nlc == 2 || nlc == 3) && nx >= 192 && big) variant = 21;
   }

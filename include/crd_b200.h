@@ -183,7 +183,7 @@ int crd_grid_set_overlap(crd_grid *g, int on);
  * erk_evolve slot of crd_nv_fused_ops() (crd_ark.h).  Returns 0 when it ran, > 0 when it does not apply (several
  * ranks, a mesh beyond the automatic size limit, a method wider than 5 stages), < 0 on failure. */
 int crd_erk_evolve(struct crd_erk_state *st, void *user_data);
-/* mode: 0 automatic (default: meshes of up to 4 Mi points), 1 whenever it applies, -1 never */
+/* mode: 0 automatic (default: meshes of up to 1 Mi points, whose working set stays in L2), 1 whenever it applies, -1 never */
 int crd_grid_set_resident(crd_grid *g, int mode);
 /* how many times the resident loop was launched on this grid */
 int64_t crd_grid_resident_launches(const crd_grid *g);

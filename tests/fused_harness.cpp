@@ -30,6 +30,7 @@ static inline double seed_model(double x) {
 #define CRD_FUSED_HOST_TEST   // take the device branch of dd_merge (intrinsics = the shims above)
 #include "crd_fused.cuh"
 #undef asm
+#include "crd_grid.cuh"   // stream_seg_rows (host code)
 
 using namespace crd;
 
@@ -67,6 +68,8 @@ double fh_rcp(double x, double seed_err) { g_seed_err = seed_err; return rcp_rn(
 int fh_rcp_in_range(double x) { return rcp_rn_in_range(x) ? 1 : 0; }
 
 // sum of non-negative terms the way the kernels do it: `lanes` interleaved accumulators (dd_add), merged pairwise (dd_merge)
+int fh_stream_seg_rows(long nyl, long strips, long ctas) { return stream_seg_rows(nyl, strips, ctas); }
+
 double fh_dd_sum(const double *q, long n, int lanes) {
   double hi[1024], lo[1024];
   if (lanes > 1024) lanes = 1024;

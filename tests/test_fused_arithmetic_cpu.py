@@ -31,6 +31,7 @@ def fh(tmp_path_factory):
     lib.fh_rcp.restype = D
     lib.fh_rcp.argtypes = [D, D]
     lib.fh_rcp_in_range.argtypes = [D]
+    lib.fh_stream_seg_rows.argtypes = [L, L, L]
     lib.fh_dd_sum.restype = D
     lib.fh_dd_sum.argtypes = [P, L, I]
     return lib
@@ -118,3 +119,23 @@ def test_branch_free_reciprocal_equals_the_ieee_quotient(fh):
     # outside the guarded range the IEEE division itself is used
     for x in (1e-300, 1e300, 5e-324, 0.0, float("inf")):
         assert not fh.fh_rcp_in_range(x)
+
+
+def test_streaming_kernel_segments_fill_whole_waves(fh):
+    """stream_seg_rows (crd_grid.cuh): the persistent CTAs take the units (strips x row segments) round-robin, so a launch lasts
+    ceil(units / ctas) unit times.  The chosen segment length must keep that within a few per cent of the ideal share of rows per
+    CTA (plus the two extra rows a segment fetches) for meshes from one million points up, with segments of at least 16 rows."""
+    for ctas in (296, 444):
+        for nx, nyl in ((1000, 4000), (1024, 4096), (1400, 5600), (2048, 8192), (4096, 16384), (16384, 2048), (16384, 16384),
+                        (8192, 4096), (8192, 32768), (520, 2100), (320, 3400), (16384, 512), (777, 12345)):
+            strips = (nx + 255) // 256
+            rows = fh.fh_stream_seg_rows(nyl, strips, ctas)
+            assert 16 <= rows <= 512
+            nseg = -(-nyl // rows)
+            waves = -(-strips * nseg // ctas)
+            cost = waves * (rows + 2)
+            ideal = strips * nyl / ctas
+            assert cost <= 1.12 * ideal + 24, (ctas, nx, nyl, rows, cost, ideal)
+            fixed = -(-strips * -(-nyl // 128) // ctas) * 130          # the fixed 128-row segments this replaces
+            assert cost <= fixed
+    assert fh.fh_stream_seg_rows(5, 2, 444) == 5 and fh.fh_stream_seg_rows(100, 1, 444) == 16

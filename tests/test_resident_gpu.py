@@ -154,7 +154,7 @@ def test_default_meshes_use_the_resident_loop_and_large_ones_do_not(crd, ctx):
     assert s.ARKode(1.0, crd.ARK_ONE_STEP)[0] == 0 and s.ARKode(1.0, crd.ARK_ONE_STEP)[0] == 0 and grid.resident_launches == 0
     assert s.stats()["nst"] == 2
     s.free(); grid.close()
-    nx, ny = 2048, 2304    # > 4 Mi points: HBM-bound, stays with the TMA-tiled launch-per-stage path
+    nx, ny = 2048, 2304    # > 1 Mi points: beyond L2, stays with the launch-per-stage path
     grid = crd.Grid(ctx, crd.make_params("fhn_torus", nx, ny))
     y = grid.new_vector()
     grid.fill_synthetic(y)
