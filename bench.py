@@ -426,16 +426,25 @@ def flat_models_block(crd, ctx, peaks, arith, arith_name, steps, warmup):
     return out
 
 
-def copy_ceiling(torch, nbytes, reps=3):
+def copy_ceiling(torch, nbytes, reps=3, host_in=None, host_out=None):
     """What the PCIe / host-memory path allows with no kernel in between: one H2D and one D2H cudaMemcpyAsync of `nbytes` each,
     from / into page-locked host memory, in flight together on two streams (the traffic of one e2e step).  Timed like the e2e
-    leg: one warm-up, then the MEAN over `reps` back-to-back repetitions (the caller takes the max over ranks)."""
+    leg: one warm-up, then the MEAN over `reps` back-to-back repetitions (the caller takes the max over ranks).
+    host_in / host_out: addresses of the e2e leg's own page-locked buffers (same pages, same NUMA placement); fresh ones if absent."""
+    import ctypes as C
     n = nbytes // 8
-    h_in = torch.empty(n, dtype=torch.float64, pin_memory=True)
-    h_out = torch.empty(n, dtype=torch.float64, pin_memory=True)
+
+    def wrap(addr):
+        t = torch.frombuffer((C.c_double * n).from_address(addr), dtype=torch.float64)
+        return t if t.is_pinned() else None
+    h_in = wrap(host_in) if host_in else None
+    h_out = wrap(host_out) if host_out else None
+    if h_in is None or h_out is None:
+        h_in = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        h_out = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        h_in.zero_()
     d_in = torch.empty(n, dtype=torch.float64, device="cuda")
     d_out = torch.zeros(n, dtype=torch.float64, device="cuda")
-    h_in.zero_()
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 
     def once():
@@ -655,17 +664,19 @@ def main():
     grid.f(T_EVAL, y, ydot)
     crd._lib.check(lib.crd_memcpy_d2h(ctx._h, ref.ctypes.data, ydot.device_ptr, ref.nbytes), "read back")
     e2e_ok = bool(probe.tobytes() == ref.tobytes())
-    lib.crd_free_host(hy); lib.crd_free_host(hd)
-    # the same bytes with no kernel in between, all ranks copying at once: the ceiling of this box's PCIe / host-memory path
+    del probe
+    # the same bytes, from / into the same host buffers, with no kernel in between, all ranks copying at once: the ceiling of
+    # this box's PCIe / host-memory path
     ceiling = None
     try:
         barrier()
-        c_s = max_over_ranks(copy_ceiling(torch, nbytes, max(1, args.e2e_steps)))
+        c_s = max_over_ranks(copy_ceiling(torch, nbytes, max(1, args.e2e_steps), hy, hd))
         ceiling = {"ms_per_step": 1e3 * c_s, "GBs_each_way_per_gpu": nbytes / c_s / 1e9,
-                   "what": "one cudaMemcpyAsync H2D + one D2H of the step's bytes from / to page-locked memory, concurrently, on all %d rank(s) at once; "
+                   "what": "one cudaMemcpyAsync H2D + one D2H of the step's bytes from / to the e2e leg's own page-locked buffers, concurrently, on all %d rank(s) at once; "
                            "mean over %d repetitions after a warm-up, max over ranks (timed like the e2e leg)" % (world, max(1, args.e2e_steps))}
     except Exception as e:
         ceiling = {"error": str(e)[:160]}
+    lib.crd_free_host(hy); lib.crd_free_host(hd)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
            "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "matches_device_result": e2e_ok,
            "api": "crd_rhs_host (C ABI, pinned host buffers, chunked 3-stream pipeline)", "copy_ceiling": ceiling, "numa": numa}

@@ -436,7 +436,7 @@ int crd_rhs_host(crd_grid *g, double t, const double *y_host, double *ydot_host)
     CRD_CUDA(cudaMemcpyAsync(ydot_host + 2 * r0 * nx, g->stage_ydot + 2 * r0 * nx, row_bytes * (r1 - r0), cudaMemcpyDeviceToHost, g->s_out));
   }
   CRD_CUDA(cudaStreamSynchronize(g->s_out));
-  CRD_CUDA(cudaStreamSynchronize(sk));
+  if (sync_stream(g->ctx, "crd_rhs_host")) return -1;   // (also the place where a neighbour's rows that never arrived surface)
   g->rhs_count++;
   return 0;
 }
