@@ -206,14 +206,17 @@ def test_phi_split_is_bitwise_invariant(crd, ctx, oracle):
                     g.close()
 
 
-@pytest.mark.parametrize("variant", [13, 15, 20, 21, 0])
-def test_exchange_inside_the_launch(crd, oracle, variant):
+@pytest.mark.parametrize("variant,mesh", [(13, (520, 1400)), (15, (520, 1400)), (20, (520, 1400)), (21, (520, 1400)), (0, (520, 1400)),
+                                          (21, (1030, 8300)), (0, (1030, 8300))])
+def test_exchange_inside_the_launch(crd, oracle, variant, mesh):
     """crd_rhs on a connected grid: ONE launch per evaluation — its first CTAs push the boundary rows to the neighbours, the
     tiles / row segments that touch a ghost row come last and acquire their strip's flag.  Two and three ranks emulated on one
     GPU, each with its own context (stream), so the launches run concurrently and really wait for each other; plain states
     and fused stage states (their combination is what gets pushed); several epochs through the double-buffered ghost rows.
     Gathered result bit-identical to the single slab."""
-    model, nx, ny = "fhn_torus", 520, 1400
+    # (1030 x 8300: slabs of a few million points, whose streaming-kernel segments are sized to fill whole waves; the automatic
+    # choice there is the tiled kernel for the plain state and the streaming kernel for the fused stage)
+    model, (nx, ny) = "fhn_torus", mesh
     y = oracle.fill_state(model, 2 * nx * ny, seed=5)
     x2 = oracle.fill_state(model, 2 * nx * ny, seed=6)
     c0 = crd.Context(0)
@@ -244,7 +247,7 @@ def test_exchange_inside_the_launch(crd, oracle, variant):
                 grids[r].f(t, ys[r], ds[r])           # asynchronous: every rank's launch is in flight before anyone is waited for
             for c in ctxs:
                 c.sync()
-            if variant != 0:                          # (0 = automatic: this mesh takes the direct kernel and the separate launches)
+            if variant != 0 or nx * ny // nr >= (2 << 20):   # (automatic on the small mesh: the direct kernel and separate launches)
                 assert [c.launches - a for c, a in zip(ctxs, l0)] == [1] * nr
             got = np.concatenate([d.to_numpy() for d in ds])
             assert got.tobytes() == want.tobytes(), (variant, nr, t)
@@ -464,3 +467,44 @@ def test_last_stage_fused_with_the_finish_equals_stage_then_finish(crd, ctx, mod
         crd.N_VConst(0.5, v)
     assert small.f_lincomb_finish(50.0, c, hb, hd, Xs, small.new_vector(), rtol, atol)[0] == 1
     small.close(); grid.close()
+
+
+@pytest.mark.parametrize("model", ["fhn_torus", "gb_flat"])
+def test_streaming_kernel_with_wave_filling_segments(crd, ctx, model):
+    """A mesh of a few million points: the streaming kernel cuts its strips into segments that fill whole waves of the
+    persistent CTAs (stream_seg_rows: here 47-row segments, the last one 11 rows, 5 strips with the last one 6 columns wide).
+    Plain state, 2- and 3-vector stages through the streaming kernel (2 and 3 CTAs per SM) and the automatic choice against the
+    direct kernel, and the fused finish against stage + N_VErkFinish: bit for bit (EXACT)."""
+    nx, ny = 1030, 4100
+    grid = crd.Grid(ctx, crd.make_params(model, nx, ny, t_boundary=38.0))
+    rng = np.random.default_rng(11)
+    n = 2 * nx * ny
+    lo, hi = (-2.0, 2.0) if model.startswith("fhn") else (0.1, 1.6)
+    X = [crd.NVector.from_numpy(ctx, rng.uniform(lo, hi, n))] + [crd.NVector.from_numpy(ctx, rng.uniform(-1.0, 1.0, n)) for _ in range(4)]
+    d1, d2 = grid.new_vector(), grid.new_vector()
+    h = 1e-3
+    for t in (10.0, 50.0):
+        for ncomb, coefs in ((0, None), (2, [1.0, 0.5 * h]), (3, [1.0, 0.25 * h, 0.25 * h])):
+            def ev(out):
+                if ncomb == 0:
+                    grid.f(t, X[0], out)
+                else:
+                    grid.f_lincomb(t, coefs, X[:ncomb], out)
+            grid.set_variant(1)
+            ev(d1)
+            want = d1.to_numpy().tobytes()
+            for variant in (0, 20, 21):
+                grid.set_variant(variant)
+                ev(d2)
+                assert d2.to_numpy().tobytes() == want, (model, t, ncomb, variant)
+        grid.set_variant(0)
+        c = [1.0, h * 5 / 32, h * 7 / 32, h * 13 / 32, -h / 32]
+        hb = [h / 6, h / 3, h / 3, h / 6, 0.0]
+        hd = [h * (1 / 6 + 0.5), h * (1 / 3 - 7 / 3), h * (1 / 3 - 7 / 3), h * (1 / 6 - 13 / 6), h * 16 / 3]
+        grid.f_lincomb(t, c, X, d1)
+        e2, y2 = crd.N_VErkFinish(hb, hd, X[0], X[1:] + [d1], d2, 1e-5, 1e-10, exact=True)
+        got = grid.new_vector()
+        rc, fe2, fy2 = grid.f_lincomb_finish(t, c, hb, hd, X, got, 1e-5, 1e-10)
+        assert rc == 0 and got.to_numpy().tobytes() == d2.to_numpy().tobytes() and fe2 == e2
+        got.destroy()
+    grid.close()
