@@ -89,6 +89,8 @@ SIGNATURES = {
     "crd_f_lincomb": (I, [D, I, c_double_p, C.POINTER(P), P, P]),
     "crd_rhs_lincomb_finish": (I, [P, D, I, c_double_p, c_double_p, c_double_p, C.POINTER(P), P, D, D, c_double_p]),
     "crd_f_lincomb_finish": (I, [D, I, c_double_p, c_double_p, c_double_p, C.POINTER(P), P, D, D, c_double_p, P]),
+    "crd_rhs_pair": (I, [P, D, D, D, P, P, P]),
+    "crd_f_pair": (I, [D, D, D, P, P, P, P]),
     "crd_grid_rhs_count": (C.c_int64, [P]),
     "crd_grid_set_variant": (I, [P, I]),
     "crd_grid_set_overlap": (I, [P, I]),
@@ -186,6 +188,7 @@ SIGNATURES = {
     "crd_ARKodeSetReuseFirstStage": (I, [P, I]),
     "crd_ARKodeSetResident": (I, [P, I]),
     "crd_ARKodeSetStageFinish": (I, [P, I]),
+    "crd_ARKodeSetStagePair": (I, [P, I]),
     "crd_ARKodeSetInitStep": (I, [P, D]),
     "crd_ARKodeSetFixedStep": (I, [P, D]),
     "crd_ARKodeGetButcherTable": (I, [P, P, P, P, c_double_p, c_double_p, c_double_p, c_double_p]),

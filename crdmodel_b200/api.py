@@ -324,6 +324,13 @@ class Grid:
             check(rc, "crd_rhs_lincomb_finish")
         return rc, out[0], out[1]
 
+    def f_pair(self, t1, t2, c, y, f1, f2):
+        """f1 = f(t1, y) and f2 = f(t2, y + c f1) in one pass over y; returns 0, or 1 when it does not apply to this grid."""
+        rc = lib().crd_rhs_pair(self._h, t1, t2, c, _ptr(y), _ptr(f1), _ptr(f2))
+        if rc < 0:
+            check(rc, "crd_rhs_pair")
+        return rc
+
     def post_halo(self, y):
         check(lib().crd_rhs_post_halo(self._h, _ptr(y)), "crd_rhs_post_halo")
 
@@ -404,7 +411,7 @@ class ARKodeSolver:
     """The reference's ARKode call sequence (FHNmodel_torus.cpp:356-373,423,491) over the device path."""
 
     def __init__(self, grid, y, t0=0.0, rtol=1e-5, atol=1e-10, max_steps=200000, fused=True, reuse_first_stage=None,
-                 resident=True, stage_finish=True):
+                 resident=True, stage_finish=True, stage_pair=True):
         L = lib()
         self.grid, self.y = grid, y
         self.mem = C.c_void_p(check_ptr(L.ARKodeCreate(), "ARKodeCreate"))
@@ -435,6 +442,8 @@ class ARKodeSolver:
         check(L.crd_ARKodeSetResident(self.mem, 1 if resident else 0), "crd_ARKodeSetResident")
         # stage_finish: the last stage and the step finish in one pass over memory where the grid offers it (one GPU, large mesh)
         check(L.crd_ARKodeSetStageFinish(self.mem, 1 if stage_finish else 0), "crd_ARKodeSetStageFinish")
+        # stage_pair: f(tn, ynew) of an accepted step and the next step's second stage in one pass where the grid offers it
+        check(L.crd_ARKodeSetStagePair(self.mem, 1 if stage_pair else 0), "crd_ARKodeSetStagePair")
 
     _close_rank = 0
 

@@ -414,10 +414,10 @@ struct _generic_N_Vector_Ops g_ops = {
 // FAST grids: chains of fused multiply-adds.  EXACT grids: every fused entry reproduces the bits of the op-by-op sequence
 // (crd_fused.cuh); there is no fused lincomb in that table, so the rare combinations outside a step (dense output) are issued
 // op by op as well.
-const crd_fused_ops g_fused = {N_VLinearCombination_Crd, N_VErkFinish_Crd, crd_f_lincomb, crd_erk_evolve, crd_f_lincomb_finish};
-const crd_fused_ops g_fused_ops_only = {N_VLinearCombination_Crd, N_VErkFinish_Crd, nullptr, nullptr, nullptr};
-const crd_fused_ops g_fused_exact = {nullptr, N_VErkFinishSeq_Crd, crd_f_lincomb, crd_erk_evolve, crd_f_lincomb_finish};
-const crd_fused_ops g_fused_exact_ops_only = {nullptr, N_VErkFinishSeq_Crd, nullptr, nullptr, nullptr};
+const crd_fused_ops g_fused = {N_VLinearCombination_Crd, N_VErkFinish_Crd, crd_f_lincomb, crd_erk_evolve, crd_f_lincomb_finish, crd_f_pair};
+const crd_fused_ops g_fused_ops_only = {N_VLinearCombination_Crd, N_VErkFinish_Crd, nullptr, nullptr, nullptr, nullptr};
+const crd_fused_ops g_fused_exact = {nullptr, N_VErkFinishSeq_Crd, crd_f_lincomb, crd_erk_evolve, crd_f_lincomb_finish, crd_f_pair};
+const crd_fused_ops g_fused_exact_ops_only = {nullptr, N_VErkFinishSeq_Crd, nullptr, nullptr, nullptr, nullptr};
 
 }  // namespace
 

@@ -13,6 +13,7 @@
 #include <cstdlib>
 
 #include "crd_rhs_kernels.cuh"
+#include "crd_rhs_pair.cuh"
 #include "crd_tables.hpp"
 
 
@@ -360,6 +361,42 @@ int crd_f_lincomb_finish(realtype t, int s, const realtype *c, const realtype *h
   }
   if (N_VGetLocalLength_Crd(ynew) != crd_grid_local_length(g)) { set_error("crd_f_lincomb_finish: vector does not match the grid"); return -1; }
   return crd_rhs_lincomb_finish(g, t, s, c, hb, hd, xs, N_VGetDeviceArrayPointer_Crd(ynew), rtol, atol, out);
+}
+
+// f1 = f(t1, y) and f2 = f(t2, y + c f1) in one pass over y (crd_rhs_pair.cuh): the derivative at an accepted state together with
+// the second stage of the next step.  Bits of crd_rhs followed by crd_rhs_lincomb(2, (1, c), (y, f1)).  Returns 1 when it does
+// not apply (a phi-split grid, a mesh too small to stream): the caller issues the two evaluations.
+int crd_rhs_pair(crd_grid *g, double t1, double t2, double c, const double *y, double *f1, double *f2) {
+  if (!g || !y || !f1 || !f2) { set_error("crd_rhs_pair: null argument"); return -1; }
+  if (g->connected || g->nx < kPairCols || g->nyl < 8 || g->nx * g->nyl < (2LL << 20) || g->variant != 0) return 1;
+  if (y == f1 || y == f2 || f1 == f2) { set_error("crd_rhs_pair: aliased vectors"); return -1; }
+  if (use(g->ctx)) return -1;
+  PairArgs a;
+  a.y = y; a.f1 = f1; a.f2 = f2;
+  a.cth = g->cth; a.brow = g->brow;
+  a.nx = g->nx; a.nyl = g->nyl;
+  a.k = g->k;
+  a.c[0] = 1.0; a.c[1] = c;
+  a.react = (is_fhn(g->p.model) || g->p.just_diffusion == 0) ? 1 : 0;
+  const int south = g->js == 0 ? 1 : 0, north = g->je == g->ny - 1 ? 2 : 0;
+  a.frz1 = t1 < g->p.t_boundary ? (south | north) : 0;
+  a.frz2 = t2 < g->p.t_boundary ? (south | north) : 0;
+  if (launch_pair(g, a, g->ctx->stream)) return -1;
+  g->rhs_count += 2;
+  return 0;
+}
+
+// the integrator's entry (crd_fused_ops.rhs_pair): only where one pass beats the two launches — FAST arithmetic (crd_rhs_pair.cuh)
+int crd_f_pair(realtype t1, realtype t2, realtype c, N_Vector y, N_Vector f1, N_Vector f2, void *user_data) {
+  crd_grid *g = (crd_grid *)user_data;
+  if (!g || !y || !f1 || !f2) return -1;
+  if (g->p.arith != CRD_ARITH_FAST) return 1;
+  const long long len = crd_grid_local_length(g);
+  if (N_VGetLocalLength_Crd(y) != len || N_VGetLocalLength_Crd(f1) != len || N_VGetLocalLength_Crd(f2) != len) {
+    set_error("crd_f_pair: vector does not match the grid");
+    return -1;
+  }
+  return crd_rhs_pair(g, t1, t2, c, N_VGetDeviceArrayPointer_Crd(y), N_VGetDeviceArrayPointer_Crd(f1), N_VGetDeviceArrayPointer_Crd(f2));
 }
 
 int crd_f(realtype t, N_Vector y, N_Vector ydot, void *user_data) {

@@ -64,6 +64,9 @@ struct ArkMem {
   bool resident = true;     // use fused->erk_evolve when it is offered and applies
   bool resident_na = false; // it answered "does not apply" once: stop asking
   bool no_stage_finish = false;  // rhs_lincomb_finish answered "does not apply" once
+  bool no_stage_pair = false;    // rhs_pair answered "does not apply" once (or was switched off)
+  bool stage2_ready = false;     // F[1] holds stage 2 of the NEXT step, evaluated together with f(tn, yn) for the step size stage2_h
+  double stage2_h = 0.0;
 };
 
 void set_zonneveld(ArkMem *m) {
@@ -242,6 +245,11 @@ int take_step(ArkMem *m) {
       if (is == 0 && m->reuse_first) {
         m->Fp[0] = m->fnew;  // f(tn, yn), evaluated when the previous step completed
         continue;
+      }
+      if (is == 1 && m->stage2_ready) {
+        // evaluated in the same pass as f(tn, yn) when the previous step completed — for exactly this step size?
+        m->stage2_ready = false;
+        if (m->reuse_first && m->h == m->stage2_h) continue;
       }
       int r;
       if (is == m->s - 1 && is > 0 && !m->no_stage_finish && m->fused && m->fused->rhs_lincomb_finish && m->fused->erk_finish &&
@@ -467,6 +475,12 @@ int crd_ARKodeSetStageFinish(void *mem, int on) {
   ((ArkMem *)mem)->no_stage_finish = on == 0;
   return ARK_SUCCESS;
 }
+int crd_ARKodeSetStagePair(void *mem, int on) {
+  if (!mem) return ARK_MEM_NULL;
+  ((ArkMem *)mem)->no_stage_pair = on == 0;
+  ((ArkMem *)mem)->stage2_ready = false;
+  return ARK_SUCCESS;
+}
 int crd_ARKodeSetInitStep(void *mem, realtype hin) {
   if (!mem) return ARK_MEM_NULL;
   ((ArkMem *)mem)->hin = hin;
@@ -575,8 +589,19 @@ int ARKode(void *mem, realtype tout, N_Vector yout, realtype *tret, int itask) {
     nstloc++;
     m->etamax = m->growth;
     m->next_h = m->h * m->eta;
-    int r = rhs(m, m->tn, m->yn, m->fnew);
-    if (r != 0) { N_VScale(1.0, m->yn, yout); *tret = m->tn; return ARK_RHSFUNC_FAIL; }
+    int r = 1;
+    m->stage2_ready = false;
+    if (!m->no_stage_pair && m->reuse_first && m->hfixed == 0.0 && m->fused && m->fused->rhs_pair && m->s >= 2 && m->A[1][0] != 0.0) {
+      // f(tn, yn) and the next step's second stage f(tn + c2 h, yn + h a21 f(tn, yn)) in one pass over yn
+      r = m->fused->rhs_pair(m->tn, m->tn + m->c[1] * m->next_h, m->next_h * m->A[1][0], m->yn, m->fnew, m->F[1], m->user_data);
+      if (r < 0) { N_VScale(1.0, m->yn, yout); *tret = m->tn; return ARK_RHSFUNC_FAIL; }
+      if (r == 0) { m->nfe += 2; m->stage2_ready = true; m->stage2_h = m->next_h; }
+      else m->no_stage_pair = true;   // does not apply to this problem: stop asking
+    }
+    if (r != 0) {
+      r = rhs(m, m->tn, m->yn, m->fnew);
+      if (r != 0) { N_VScale(1.0, m->yn, yout); *tret = m->tn; return ARK_RHSFUNC_FAIL; }
+    }
 
     if (itask == ARK_NORMAL && (m->tn - tout) * m->h >= 0.0) {
       int dr = dense_eval(m, tout, yout);

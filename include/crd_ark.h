@@ -49,6 +49,10 @@ typedef struct crd_fused_ops {
    * calls rhs_lincomb and erk_finish), < 0 on failure.  416 instead of 528 B/point/step. */
   int (*rhs_lincomb_finish)(realtype t, int s, const realtype *c, const realtype *hb, const realtype *hd, N_Vector *X,
                             N_Vector ynew, realtype rtol, realtype atol, realtype out[2], void *user_data);
+  /* optional: f1 = f(t1, y) and f2 = f(t2, y + c f1) in one pass over y: the derivative at an accepted state (dense output, stage
+   * 1 of the next step) together with that step's second stage.  Returns 0, > 0 when it does not apply (the integrator then
+   * evaluates them one by one), < 0 on failure.  48 instead of 80 B/point. */
+  int (*rhs_pair)(realtype t1, realtype t2, realtype c, N_Vector y, N_Vector f1, N_Vector f2, void *user_data);
 } crd_fused_ops;
 
 /* The integrator's state handed to erk_evolve and taken back from it.  The callee advances (tn, yn, fnew =
@@ -94,6 +98,11 @@ int crd_ARKodeSetResident(void *arkode_mem, int on);
 /* Last stage + step finish in one pass (crd_fused_ops.rhs_lincomb_finish): on = 1 (default) uses it when offered and
  * applicable; on = 0 always issues the stage evaluation and the finish separately. */
 int crd_ARKodeSetStageFinish(void *arkode_mem, int on);
+/* f(tn, ynew) of an accepted step together with the second stage of the next step in one pass (crd_fused_ops.rhs_pair): on = 1
+ * (default) uses it when offered and applicable (needs the reuse of the first stage, an explicit second stage that depends on
+ * the first only, adaptive steps); on = 0 evaluates them one by one.  If the next step is not taken with the predicted size
+ * (a failed error test, a caller that changes it) the second stage is simply evaluated again. */
+int crd_ARKodeSetStagePair(void *arkode_mem, int on);
 /* Initial step size (0 = estimate it, the default). */
 int crd_ARKodeSetInitStep(void *arkode_mem, realtype hin);
 /* Fixed step size (no error test, no adaptivity); 0 switches adaptivity back on. */

@@ -171,6 +171,16 @@ int crd_rhs_lincomb_finish(crd_grid *g, double t, int s, const double *c, const 
                            const double *const *X_dev, double *ynew_dev, double rtol, double atol, double out[2]);
 int crd_f_lincomb_finish(realtype t, int s, const realtype *c, const realtype *hb, const realtype *hd, N_Vector *X, N_Vector ynew,
                          realtype rtol, realtype atol, realtype out[2], void *user_data);
+/* Two evaluations in one pass over the state: f1 = f(t1, y), f2 = f(t2, y + c f1) — the derivative at an accepted state
+ * (ARKode evaluates it for its dense output; it is also stage 1 of the next step) together with that step's second stage,
+ * whose state needs nothing but y and f1 (src/FHNmodel_torus.cpp:423: two of the f() calls inside ARKode()).  y is read once,
+ * y + c f1 never exists in memory: 48 instead of 80 B per point.  f1 and f2 have the bits of crd_rhs followed by
+ * crd_rhs_lincomb(2, (1, c), (y, f1)).  Returns 0, or 1 when it does not apply (a phi-split grid, a mesh too small to stream,
+ * a forced kernel variant): issue the two evaluations separately. */
+int crd_rhs_pair(crd_grid *g, double t1, double t2, double c, const double *y_dev, double *f1_dev, double *f2_dev);
+/* the integrator's form (crd_fused_ops.rhs_pair); also declines (1) on CRD_ARITH_EXACT grids, where one pass with twice the
+ * separately rounded arithmetic is bound by issue slots and no faster than the two launches */
+int crd_f_pair(realtype t1, realtype t2, realtype c, N_Vector y, N_Vector f1, N_Vector f2, void *user_data);
 /* count of RHS evaluations issued on this grid */
 int64_t crd_grid_rhs_count(const crd_grid *g);
 /* kernel variant: 0 = default; others are experimental tilings kept for profiling */

@@ -182,3 +182,26 @@ def test_large_mesh_fused_loop_takes_the_steps_of_the_cpu_run(crd, ctx, oracle):
     assert st["nst"] == nst_c and st["netf"] == cpu_trajectory.netf
     assert y.to_numpy().tobytes() == cpu[0].tobytes()
     s.free(); grid.close()
+
+
+def test_accepted_state_and_next_second_stage_in_one_pass(crd, ctx):
+    """FAST grid beyond 2 Mi points: after every accepted step f(tn, ynew) and the next step's second stage come from one pass
+    over ynew (crd_fused_ops.rhs_pair).  Same steps and the same number of evaluations per step as the loop that issues them one
+    by one (one more at the very end: the stage prepared for a step that is never taken), states equal to rounding; the device-
+    side count of evaluations shows that the pass really ran."""
+    nx, ny = 1030, 2100
+    out = {}
+    for pair in (True, False):
+        g = crd.Grid(ctx, crd.make_params("fhn_torus", nx, ny, arith=crd.ARITH_FAST, vary_beta=0, t_boundary=0.0))
+        y = g.new_vector()
+        g.fill_initial_conditions(y, 0.1, 0.5, 1, -1.25, 1.25 ** 3 - 3 * 1.25)
+        s = crd.ARKodeSolver(g, y, fused="full", resident=False, stage_pair=pair, max_steps=12)
+        flag, t = s.ARKode(1e9)
+        assert flag == -1          # the step limit
+        st = s.stats()
+        out[pair] = (y.to_numpy(), st, t)
+        s.free(); g.close()
+    (ya, sa, ta), (yb, sb, tb) = out[True], out[False]
+    assert sa["nst"] == sb["nst"] == 12 and sa["netf"] == sb["netf"] and abs(ta - tb) <= 1e-9 * abs(tb)
+    assert sa["nfe"] == sb["nfe"] + 1
+    assert np.abs(ya - yb).max() <= 1e-11 * (1.0 + np.abs(yb).max())

@@ -508,3 +508,36 @@ def test_streaming_kernel_with_wave_filling_segments(crd, ctx, model):
         assert rc == 0 and got.to_numpy().tobytes() == d2.to_numpy().tobytes() and fe2 == e2
         got.destroy()
     grid.close()
+
+
+@pytest.mark.parametrize("model,arith", [("fhn_torus", "exact"), ("fhn_torus", "fast"), ("gb_torus", "exact"), ("fhn_flat", "exact"), ("gb_flat", "fast")])
+@pytest.mark.parametrize("nx,ny", [(1030, 2100), (481, 4400)])
+def test_two_evaluations_in_one_pass(crd, ctx, model, arith, nx, ny):
+    """crd_rhs_pair: f1 = f(t1, y) and f2 = f(t2, y + c f1) from one pass over y, against crd_rhs followed by crd_rhs_lincomb —
+    bit for bit in EXACT arithmetic (same device functions), to rounding in FAST.  Strips of 240 columns whose last one is 70 / 1 columns wide, the
+    periodic columns fetched as one or two wrapped pieces, segments that do not divide the rows, frozen boundary rows in both,
+    one or neither evaluation."""
+    ar = crd.ARITH_EXACT if arith == "exact" else crd.ARITH_FAST
+    grid = crd.Grid(ctx, crd.make_params(model, nx, ny, arith=ar, t_boundary=38.0))
+    rng = np.random.default_rng(3)
+    lo, hi = (-2.0, 2.0) if model.startswith("fhn") else (0.1, 1.6)
+    y = crd.NVector.from_numpy(ctx, rng.uniform(lo, hi, 2 * nx * ny))
+    f1, f2, w1, w2 = (grid.new_vector() for _ in range(4))
+    c = 0.5e-3
+    for t1, t2 in ((10.0, 10.3), (37.9, 38.2), (50.0, 50.1)):
+        crd.N_VConst(-7.0, f1); crd.N_VConst(-7.0, f2)
+        assert grid.f_pair(t1, t2, c, y, f1, f2) == 0
+        grid.f(t1, y, w1)
+        grid.f_lincomb(t2, [1.0, c], [y, w1], w2)
+        if arith == "exact":
+            assert f1.to_numpy().tobytes() == w1.to_numpy().tobytes(), (model, arith, t1)
+            assert f2.to_numpy().tobytes() == w2.to_numpy().tobytes(), (model, arith, t2)
+        else:       # FAST: the compiler contracts each kernel's expressions on its own; equal to rounding
+            for got, want in ((f1, w1), (f2, w2)):
+                a, b = got.to_numpy(), want.to_numpy()
+                assert np.abs(a - b).max() <= 1e-12 * (1.0 + np.abs(b).max()), (model, arith, t1)
+    # does not apply: a small mesh, a phi-split grid (the caller evaluates one by one)
+    small = crd.Grid(ctx, crd.make_params(model, 300, 400, arith=ar))
+    v = [small.new_vector() for _ in range(3)]
+    assert small.f_pair(1.0, 1.1, c, *v) == 1
+    small.close(); grid.close()
