@@ -368,7 +368,7 @@ int crd_f_lincomb_finish(realtype t, int s, const realtype *c, const realtype *h
 // not apply (a phi-split grid, a mesh too small to stream): the caller issues the two evaluations.
 int crd_rhs_pair(crd_grid *g, double t1, double t2, double c, const double *y, double *f1, double *f2) {
   if (!g || !y || !f1 || !f2) { set_error("crd_rhs_pair: null argument"); return -1; }
-  if (g->connected || g->nx < kPairCols || g->nyl < 8 || g->nx * g->nyl < (2LL << 20) || g->variant != 0) return 1;
+  if (g->connected || g->nx < kPairCols || g->nyl < 32 || g->nx * g->nyl < (1LL << 20) || g->variant != 0) return 1;
   if (y == f1 || y == f2 || f1 == f2) { set_error("crd_rhs_pair: aliased vectors"); return -1; }
   if (use(g->ctx)) return -1;
   PairArgs a;
@@ -386,11 +386,13 @@ int crd_rhs_pair(crd_grid *g, double t1, double t2, double c, const double *y, d
   return 0;
 }
 
-// the integrator's entry (crd_fused_ops.rhs_pair): only where one pass beats the two launches — FAST arithmetic (crd_rhs_pair.cuh)
+// the integrator's entry (crd_fused_ops.rhs_pair): only where one pass beats the two launches — FAST arithmetic everywhere
+// (x1.45-1.8), EXACT arithmetic up to 32 Mi points (x1.07-1.27: fewer launches, one read of ynew); beyond that the EXACT pass is
+// compute-bound under the power cap and level with the two launches (crd_rhs_pair.cuh, profiles/README.md)
 int crd_f_pair(realtype t1, realtype t2, realtype c, N_Vector y, N_Vector f1, N_Vector f2, void *user_data) {
   crd_grid *g = (crd_grid *)user_data;
   if (!g || !y || !f1 || !f2) return -1;
-  if (g->p.arith != CRD_ARITH_FAST) return 1;
+  if (g->p.arith != CRD_ARITH_FAST && (is_fhn(g->p.model) ? g->nx * g->nyl > (32LL << 20) : true)) return 1;
   const long long len = crd_grid_local_length(g);
   if (N_VGetLocalLength_Crd(y) != len || N_VGetLocalLength_Crd(f1) != len || N_VGetLocalLength_Crd(f2) != len) {
     set_error("crd_f_pair: vector does not match the grid");

@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import crdmodel_b200 as crd
 ctx = crd.Context(0)
-sizes = [(16384, 16384), (4096, 16384), (2048, 8192), (1024, 4096)]
+sizes = [(16384, 16384), (4096, 16384), (2048, 8192), (1024, 4096), (600, 2400)]
 if len(sys.argv) > 1:
     sizes = [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]]
 for model in ("fhn_torus", "gb_torus"):
