@@ -205,3 +205,31 @@ def test_accepted_state_and_next_second_stage_in_one_pass(crd, ctx):
     assert sa["nst"] == sb["nst"] == 12 and sa["netf"] == sb["netf"] and abs(ta - tb) <= 1e-9 * abs(tb)
     assert sa["nfe"] == sb["nfe"] + 1
     assert np.abs(ya - yb).max() <= 1e-11 * (1.0 + np.abs(yb).max())
+
+
+def test_one_pass_pair_keeps_exact_trajectories_bit_identical(crd, ctx):
+    """EXACT FHN grid of a few million points, several ARKode calls with dense output in between (the prepared second stage
+    survives the return to the caller), an error-test failure on the way (the prepared stage is discarded and evaluated again for
+    the smaller step): states returned at every output time, step counts and the final state are bit-identical with and without
+    the pass."""
+    nx, ny = 1030, 1100
+    out = {}
+    for pair in (True, False):
+        g = crd.Grid(ctx, crd.make_params("fhn_torus", nx, ny, vary_beta=0, t_boundary=0.0))
+        y = g.new_vector()
+        g.fill_initial_conditions(y, 0.1, 0.5, 1, -1.25, 1.25 ** 3 - 3 * 1.25)
+        s = crd.ARKodeSolver(g, y, fused="full", resident=False, stage_pair=pair)
+        s.set_init_step(2e-2)        # too large for the front: the first attempts fail the error test
+        res = []
+        for tout in (0.05, 0.11, 0.2):
+            flag, t = s.ARKode(tout)
+            assert flag == 0 and t == tout
+            res.append(y.to_numpy().copy())
+        st = s.stats()
+        out[pair] = (res, st)
+        s.free(); g.close()
+    (ra, sa), (rb, sb) = out[True], out[False]
+    assert sa["nst"] == sb["nst"] and sa["netf"] == sb["netf"] and sa["netf"] > 0 and sa["nst_attempts"] == sb["nst_attempts"]
+    for a, b in zip(ra, rb):
+        assert a.tobytes() == b.tobytes()
+    assert sb["nfe"] <= sa["nfe"] <= sb["nfe"] + 1
