@@ -386,13 +386,13 @@ int crd_rhs_pair(crd_grid *g, double t1, double t2, double c, const double *y, d
   return 0;
 }
 
-// the integrator's entry (crd_fused_ops.rhs_pair): only where one pass beats the two launches — FAST arithmetic everywhere
-// (x1.45-1.8), EXACT arithmetic up to 32 Mi points (x1.07-1.27: fewer launches, one read of ynew); beyond that the EXACT pass is
-// compute-bound under the power cap and level with the two launches (crd_rhs_pair.cuh, profiles/README.md)
+// the integrator's entry (crd_fused_ops.rhs_pair): only where one pass beats the two launches — every FAST grid (x1.45-1.8) and
+// EXACT grids of the FHN programs (x1.1-1.35); the Goldbeter kinetics in EXACT arithmetic are bound by FP64 work and the pass is
+// slower than the two launches there (crd_rhs_pair.cuh, profiles/README.md)
 int crd_f_pair(realtype t1, realtype t2, realtype c, N_Vector y, N_Vector f1, N_Vector f2, void *user_data) {
   crd_grid *g = (crd_grid *)user_data;
   if (!g || !y || !f1 || !f2) return -1;
-  if (g->p.arith != CRD_ARITH_FAST && (is_fhn(g->p.model) ? g->nx * g->nyl > (32LL << 20) : true)) return 1;
+  if (g->p.arith != CRD_ARITH_FAST && !is_fhn(g->p.model)) return 1;
   const long long len = crd_grid_local_length(g);
   if (N_VGetLocalLength_Crd(y) != len || N_VGetLocalLength_Crd(f1) != len || N_VGetLocalLength_Crd(f2) != len) {
     set_error("crd_f_pair: vector does not match the grid");

@@ -17,10 +17,11 @@
 // Applies to a slab that wraps onto itself (one rank); a phi-split grid keeps the two separate evaluations.
 //
 // Measured at 16384 x 16384 (profiles/README.md): FAST arithmetic 1.89 ms = 6.8 TB/s at 48 B/point against 3.3-3.4 ms for the two
-// launches (x1.75; a first, streaming form of this pass — persistent CTAs, row ring — reached 2.41 ms); EXACT arithmetic
-// 3.15-3.7 ms against 3.4-3.6 ms: two evaluations' worth of separately rounded operations, exact constant divisions and range
-// checks per 48 B make the pass compute-bound and the power cap does the rest, so nothing is gained and the integrator
-// (crd_f_pair) keeps the two launches on EXACT grids; the kernel is there and tested bit for bit all the same (crd_rhs_pair).
+// launches (x1.75; a first, streaming form of this pass — persistent CTAs, row ring — reached 2.41 ms); EXACT arithmetic (FHN)
+// 2.67 ms in a burst, 3.16 ms warm, against 3.45-3.8 ms: two evaluations' worth of separately rounded operations, exact constant
+// divisions and range checks per 48 B make the pass latency-bound, not memory-bound.  Goldbeter in EXACT arithmetic is bound
+// by FP64 work (2 x 69 operations per point) and stays slower than its two launches (1.2-1.3 against 1.05-1.1 ms at 4096 x
+// 16384): the integrator's entry (crd_f_pair) declines there; the kernel is tested bit for bit all the same (crd_rhs_pair).
 #pragma once
 #include "crd_rhs_kernels.cuh"
 
@@ -40,11 +41,11 @@ struct PairArgs {
 
 constexpr int kPairCols = 240;            // columns a tile writes (8 warps x 30)
 constexpr int kPairPitch = kPairCols + 4; // points per staged row: two columns of y on either side
-constexpr int kPairTY = 12;               // rows a tile writes (its 16 staged rows of 244 points are 62 KB: three CTAs per SM)
+constexpr int kPairTY = 12;               // rows a FAST tile writes (its 16 staged rows of 244 points are 62 KB: three CTAs per SM)
 
-template <int MODEL, bool EXACT, int MINB>
+template <int MODEL, bool EXACT, int MINB, int TY = kPairTY>
 __global__ void __launch_bounds__(256, MINB) rhs_pair_tile_kernel(const PairArgs a) {
-  constexpr int PITCH = kPairPitch, TY = kPairTY, ROWS = TY + 4;
+  constexpr int PITCH = kPairPitch, ROWS = TY + 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2 *tile = reinterpret_cast<double2 *>(smem_raw);                  // [ROWS][PITCH]
   const unsigned bar = smem_u32(smem_raw + (size_t)ROWS * PITCH * 16);
@@ -151,22 +152,29 @@ __global__ void __launch_bounds__(256, MINB) rhs_pair_tile_kernel(const PairArgs
   }
 }
 
-template <int MODEL, bool EXACT>
-int launch_pair_tile(crd_grid *g, const PairArgs &a, cudaStream_t st) {
-  constexpr int MINB = 3;
-  const long long strips = (a.nx + kPairCols - 1) / kPairCols, tiles = strips * ((a.nyl + kPairTY - 1) / kPairTY);
+template <int MODEL, bool EXACT, int MINB, int TY>
+int launch_pair_tile_shape(crd_grid *g, const PairArgs &a, cudaStream_t st) {
+  const long long strips = (a.nx + kPairCols - 1) / kPairCols, tiles = strips * ((a.nyl + TY - 1) / TY);
   if (tiles > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
-  const size_t smem = (size_t)(kPairTY + 4) * kPairPitch * 16 + 16;
-  auto kern = rhs_pair_tile_kernel<MODEL, EXACT, MINB>;
+  const size_t smem = (size_t)(TY + 4) * kPairPitch * 16 + 16;
+  auto kern = rhs_pair_tile_kernel<MODEL, EXACT, MINB, TY>;
   static bool attr_set[64] = {};
   const int dev = g->ctx->device & 63;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110000);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113000);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
     attr_set[dev] = true;
   }
   kern<<<(unsigned)tiles, 256, smem, st>>>(a);
   return check_launch(g->ctx, "rhs_pair_tile_kernel");
+}
+// FAST arithmetic is bound by memory: 12-row tiles (the smallest frame), three CTAs per SM.  EXACT arithmetic is bound by the
+// latency of its dependent FP64 chains: 8-row tiles fit four CTAs per SM at 64 registers, and 32 instead of 24 warps per SM are
+// worth more than the larger frame costs (2.67-3.16 against 3.21-3.67 ms at 16384^2; 10-row tiles: 2.73-3.2 ms).
+template <int MODEL, bool EXACT>
+int launch_pair_tile(crd_grid *g, const PairArgs &a, cudaStream_t st) {
+  if (EXACT) return launch_pair_tile_shape<MODEL, EXACT, 4, 8>(g, a, st);
+  return launch_pair_tile_shape<MODEL, EXACT, 3, kPairTY>(g, a, st);
 }
 
 template <int MODEL, bool EXACT>

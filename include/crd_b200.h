@@ -179,8 +179,7 @@ int crd_f_lincomb_finish(realtype t, int s, const realtype *c, const realtype *h
  * a forced kernel variant): issue the two evaluations separately. */
 int crd_rhs_pair(crd_grid *g, double t1, double t2, double c, const double *y_dev, double *f1_dev, double *f2_dev);
 /* the integrator's form (crd_fused_ops.rhs_pair); also declines (1) where the pass is not faster than the two launches:
- * CRD_ARITH_EXACT grids of the Goldbeter programs (bound by FP64 work) and of more than 32 Mi points (compute-bound under the
- * power cap) */
+ * CRD_ARITH_EXACT grids of the Goldbeter programs (bound by FP64 work) */
 int crd_f_pair(realtype t1, realtype t2, realtype c, N_Vector y, N_Vector f1, N_Vector f2, void *user_data);
 /* count of RHS evaluations issued on this grid */
 int64_t crd_grid_rhs_count(const crd_grid *g);
