@@ -47,6 +47,7 @@ constexpr int kHaloStrip = 256;
 struct HaloSync {
   double *push_prev = nullptr;                    // prev rank's north ghost row of this epoch: receives this slab's row 0
   double *push_next = nullptr;                    // next rank's south ghost row: receives this slab's last row
+  double *push2_prev = nullptr, *push2_next = nullptr;   // their second ghost rows: this slab's row 1 / row nyl-2 (pair pass only)
   unsigned long long *flag_prev = nullptr;        // their per-strip flags
   unsigned long long *flag_next = nullptr;
   const unsigned long long *wait_south = nullptr; // this grid's per-strip flags: acquire before the south / north ghost row is read
@@ -86,8 +87,10 @@ struct HaloLayout {
   long long nx;
   __host__ __device__ long long nstrips() const { return (nx + kHaloStrip - 1) / kHaloStrip; }
   __host__ __device__ size_t ghost_off(int parity, int side) const { return (size_t)(parity * 2 + side) * (size_t)nx * 2 * sizeof(double); }
+  // the second row beyond the slab on that side (only the pass that forms two evaluations at once exchanges it)
+  __host__ __device__ size_t ghost2_off(int parity, int side) const { return (size_t)(4 + parity * 2 + side) * (size_t)nx * 2 * sizeof(double); }
   __host__ __device__ size_t flag_off(int side) const {
-    return (size_t)4 * (size_t)nx * 2 * sizeof(double) + 128 + (size_t)side * (((size_t)nstrips() * 8 + 127) / 128 * 128);
+    return (size_t)8 * (size_t)nx * 2 * sizeof(double) + 128 + (size_t)side * (((size_t)nstrips() * 8 + 127) / 128 * 128);
   }
   __host__ __device__ size_t bytes() const { return flag_off(2); }
 };
@@ -125,7 +128,8 @@ struct crd_grid {
   double dx = 0, dy = 0, R = 0, r = 0, xmin = 0, xmax = 0, ymin = 0, ymax = 0;
   crd::RhsConst k{};
   double *cth = nullptr;
-  double *brow = nullptr;
+  double *brow = nullptr;          // per-phi beta of local row 0 .. nyl-1 (brow[-1], brow[nyl]: the rows of the neighbouring ranks)
+  double *brow_alloc = nullptr;    // the allocation: brow - 1
   // halo ring
   char *halo_local = nullptr;
   char *halo_prev = nullptr, *halo_next = nullptr;  // peer-mapped (or local) ghost blocks of the neighbours

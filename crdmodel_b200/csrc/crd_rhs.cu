@@ -43,13 +43,14 @@ crd_grid *crd_grid_create(crd_ctx *ctx, const crd_params *p) {
   grid_host_tables(g, cth, brow);
   cudaError_t e;
   if ((e = cudaMalloc(&g->cth, cth.size() * sizeof(double))) != cudaSuccess ||
-      (e = cudaMalloc(&g->brow, brow.size() * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&g->brow_alloc, brow.size() * sizeof(double))) != cudaSuccess ||
       (e = cudaMemcpy(g->cth, cth.data(), cth.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemcpy(g->brow, brow.data(), brow.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
+      (e = cudaMemcpy(g->brow_alloc, brow.data(), brow.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
     set_error("crd_grid_create: %s", cudaGetErrorString(e));
     crd_grid_destroy(g);
     return nullptr;
   }
+  g->brow = g->brow_alloc + 1;   // local row 0; brow[-1] and brow[nyl] are the neighbouring ranks' rows
   // ghost block + push ticket
   HaloLayout L{g->nx};
   if ((e = cudaMalloc(&g->halo_local, L.bytes())) != cudaSuccess ||
@@ -67,7 +68,7 @@ void crd_grid_destroy(crd_grid *g) {
   cudaStreamSynchronize(g->ctx->stream);
   if (g->prev_ipc && g->halo_prev) cudaIpcCloseMemHandle(g->halo_prev);
   if (g->next_ipc && g->halo_next && g->halo_next != g->halo_prev) cudaIpcCloseMemHandle(g->halo_next);
-  cudaFree(g->cth); cudaFree(g->brow); cudaFree(g->halo_local);
+  cudaFree(g->cth); cudaFree(g->brow_alloc); cudaFree(g->halo_local);
   if (g->fin_partial) cudaFree(g->fin_partial);
   if (g->res_bar) cudaFree(g->res_bar);
   if (g->res_partial) cudaFree(g->res_partial);
@@ -365,21 +366,61 @@ int crd_f_lincomb_finish(realtype t, int s, const realtype *c, const realtype *h
 
 // f1 = f(t1, y) and f2 = f(t2, y + c f1) in one pass over y (crd_rhs_pair.cuh): the derivative at an accepted state together with
 // the second stage of the next step.  Bits of crd_rhs followed by crd_rhs_lincomb(2, (1, c), (y, f1)).  Returns 1 when it does
-// not apply (a phi-split grid, a mesh too small to stream): the caller issues the two evaluations.
+// not apply (a slab too small, a forced kernel variant): the caller issues the two evaluations.  On a phi-split grid the
+// neighbours first exchange two rows of y per side (one exchange for both evaluations).
 int crd_rhs_pair(crd_grid *g, double t1, double t2, double c, const double *y, double *f1, double *f2) {
   if (!g || !y || !f1 || !f2) { set_error("crd_rhs_pair: null argument"); return -1; }
-  if (g->connected || g->nx < kPairCols || g->nyl < 32 || g->nx * g->nyl < (1LL << 20) || g->variant != 0) return 1;
+  if (g->nx < kPairCols || g->nyl < 32 || g->nx * g->nyl < (1LL << 20) || g->variant != 0) return 1;
   if (y == f1 || y == f2 || f1 == f2) { set_error("crd_rhs_pair: aliased vectors"); return -1; }
   if (use(g->ctx)) return -1;
+  if (g->connected && g->epoch != g->computed) { set_error("crd_rhs_pair: previous epoch was posted but never computed"); return -1; }
   PairArgs a;
+  a.south_near = a.south_far = a.north_near = a.north_far = nullptr;
+  a.nx = g->nx; a.nyl = g->nyl;
+  if (g->connected) {
+    // one exchange for both evaluations: two rows of y per side (the first evaluation on the adjacent ghost row is repeated
+    // locally), as launches of their own in front of the pass.  Every kernel of the sequence is loaded before the first of them
+    // is launched: the neighbours' wait kernels spin on this rank's rows, and a module load in between could wait for them.
+    if (launch_pair(g, a, g->ctx->stream, true)) return -1;
+    {
+      static bool loaded[64] = {};
+      const int dev = g->ctx->device & 63;
+      if (!loaded[dev]) {
+        cudaFuncAttributes fa;
+        CRD_CUDA(cudaFuncGetAttributes(&fa, halo_push2_kernel));
+        CRD_CUDA(cudaFuncGetAttributes(&fa, halo_wait_kernel));
+        loaded[dev] = true;
+      }
+    }
+    g->epoch++;
+    HaloLayout L{g->nx};
+    const int par = (int)(g->epoch & 1ULL);
+    RhsArgs h;
+    std::memset(&h, 0, sizeof h);
+    h.y = y; h.nx = g->nx; h.nyl = g->nyl;
+    h.hs = halo_sync(g, true, false);
+    h.hs.push2_prev = (double *)(g->halo_prev + L.ghost2_off(par, 1));
+    h.hs.push2_next = (double *)(g->halo_next + L.ghost2_off(par, 0));
+    halo_push2_kernel<<<(unsigned)L.nstrips(), 256, 0, g->ctx->stream>>>(h);
+    if (check_launch(g->ctx, "halo_push2_kernel")) return -1;
+    if (launch_wait(g, g->ctx->stream)) return -1;
+    a.south_near = (const double *)(g->halo_local + L.ghost_off(par, 0));
+    a.south_far = (const double *)(g->halo_local + L.ghost2_off(par, 0));
+    a.north_near = (const double *)(g->halo_local + L.ghost_off(par, 1));
+    a.north_far = (const double *)(g->halo_local + L.ghost2_off(par, 1));
+    g->computed = g->epoch;
+  }
   a.y = y; a.f1 = f1; a.f2 = f2;
   a.cth = g->cth; a.brow = g->brow;
   a.nx = g->nx; a.nyl = g->nyl;
   a.k = g->k;
   a.c[0] = 1.0; a.c[1] = c;
   a.react = (is_fhn(g->p.model) || g->p.just_diffusion == 0) ? 1 : 0;
+  // rows held at zero while t < tBoundary: global rows 0 and ny - 1 — local rows 0 / nyl - 1 of the first / last rank, and, seen
+  // from the other side of the periodic seam, the ghost row north of the last rank / south of the first
   const int south = g->js == 0 ? 1 : 0, north = g->je == g->ny - 1 ? 2 : 0;
-  a.frz1 = t1 < g->p.t_boundary ? (south | north) : 0;
+  const int ghosts = g->connected ? ((g->js == 0 ? 4 : 0) | (g->je == g->ny - 1 ? 8 : 0)) : 0;
+  a.frz1 = t1 < g->p.t_boundary ? (south | north | ghosts) : 0;
   a.frz2 = t2 < g->p.t_boundary ? (south | north) : 0;
   if (launch_pair(g, a, g->ctx->stream)) return -1;
   g->rhs_count += 2;

@@ -928,6 +928,24 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const RhsArgs a) {
   }
 }
 
+// two boundary rows per side of a plain state (the pass that forms two evaluations at once reads two rows beyond the slab)
+__global__ void __launch_bounds__(256) halo_push2_kernel(const RhsArgs a) {
+  const long long nstrips = (a.nx + kHaloStrip - 1) / kHaloStrip;
+  const double2 *y = reinterpret_cast<const double2 *>(a.y);
+  for (long long sp = blockIdx.x; sp < nstrips; sp += gridDim.x) {
+    const long long col = sp * kHaloStrip + threadIdx.x;
+    if (col < a.nx) {
+      reinterpret_cast<double2 *>(a.hs.push_prev)[col] = y[col];
+      reinterpret_cast<double2 *>(a.hs.push2_prev)[col] = y[a.nx + col];
+      reinterpret_cast<double2 *>(a.hs.push_next)[col] = y[(a.nyl - 1) * a.nx + col];
+      reinterpret_cast<double2 *>(a.hs.push2_next)[col] = y[(a.nyl - 2) * a.nx + col];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) halo_publish(a, sp);
+  }
+}
+
 __global__ void __launch_bounds__(256) halo_wait_kernel(const RhsArgs a) {
   const long long nstrips = (a.nx + kHaloStrip - 1) / kHaloStrip;
   for (long long q = threadIdx.x; q < 2 * nstrips; q += blockDim.x) {

@@ -14,7 +14,8 @@
 // arithmetic is the shared device code of crd_rhs_point.cuh / crd_fused.cuh: F1, z and F2 have the bits of crd_rhs followed by
 // crd_rhs_lincomb.
 //
-// Applies to a slab that wraps onto itself (one rank); a phi-split grid keeps the two separate evaluations.
+// On a phi-split grid the neighbours deliver TWO rows of y per side before the pass (halo_push2_kernel; the first evaluation on
+// the adjacent one of them is repeated here, so F1 needs no exchange of its own): push, wait, pass — three launches, one exchange.
 //
 // Measured at 16384 x 16384 (profiles/README.md): FAST arithmetic 1.89 ms = 6.8 TB/s at 48 B/point against 3.3-3.4 ms for the two
 // launches (x1.75; a first, streaming form of this pass — persistent CTAs, row ring — reached 2.41 ms); EXACT arithmetic (FHN)
@@ -36,7 +37,11 @@ struct PairArgs {
   RhsConst k;
   double c[2];            // (1, h a21): z = c[0] y + c[1] f1 in the arithmetic of the fused stage assembly
   int react;
-  int frz1, frz2;         // first / second evaluation: bit 0 = row 0, bit 1 = row nyl-1 held at zero (t < tBoundary)
+  int frz1, frz2;         // first / second evaluation: rows held at zero (t < tBoundary): bit 0 = row 0, bit 1 = row nyl-1,
+                          // bit 2 = row -1, bit 3 = row nyl (a neighbouring rank's boundary row, phi-split grid only)
+  // phi-split grid: the two rows beyond the slab on either side, delivered by the neighbours (near = adjacent row); nullptr =
+  // the slab wraps onto itself
+  const double *south_near, *south_far, *north_near, *north_far;
 };
 
 constexpr int kPairCols = 240;            // columns a tile writes (8 warps x 30)
@@ -64,9 +69,14 @@ __global__ void __launch_bounds__(256, MINB) rhs_pair_tile_kernel(const PairArgs
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(w + 4) * 16u * (unsigned)ROWS) : "memory");
     for (int r = 0; r < ROWS; ++r) {
       long long jr = (long long)jA - 2 + r;
-      jr = jr < 0 ? jr + nyl : jr >= nyl ? jr - nyl : jr;
-      if (jr >= nyl) jr -= nyl;                                            // (a partial last tile may reach two periods ahead)
-      const double2 *row = reinterpret_cast<const double2 *>(a.y) + jr * nx;
+      const double2 *row;
+      if (a.south_near && (jr < 0 || jr >= nyl)) {                         // a neighbouring rank's row
+        row = reinterpret_cast<const double2 *>(jr == -1 ? a.south_near : jr < 0 ? a.south_far : jr == nyl ? a.north_near : a.north_far);
+      } else {
+        jr = jr < 0 ? jr + nyl : jr >= nyl ? jr - nyl : jr;
+        if (jr >= nyl) jr -= nyl;                                          // (a partial last tile may reach two periods ahead)
+        row = reinterpret_cast<const double2 *>(a.y) + jr * nx;
+      }
       const unsigned dst = smem_u32(tile + (size_t)r * PITCH);
       bulk_g2s(dst + (unsigned)lwrap * 16u, row + m0, (unsigned)(m1 - m0) * 16u, bar);
       if (lwrap) bulk_g2s(dst, row + (nx - lwrap), (unsigned)lwrap * 16u, bar);
@@ -120,14 +130,14 @@ __global__ void __launch_bounds__(256, MINB) rhs_pair_tile_kernel(const PairArgs
     for (int s = 1; s <= TY + 2; ++s) {
       const int j1 = jA - 2 + s;                                           // slab row (or its periodic image) of F1 / z
       if (j1 > jB) break;
-      const int g1 = j1 < 0 ? j1 + nyli : j1 >= nyli ? j1 - nyli : j1;
+      const int g1 = a.south_near ? j1 : (j1 < 0 ? j1 + nyli : j1 >= nyli ? j1 - nyli : j1);   // (brow[-1], brow[nyl] exist)
       const double2 c = my[s * PITCH + 1];
       const double uW = my[s * PITCH].x, uE = my[s * PITCH + 2].x, uS = my[(s - 1) * PITCH + 1].x, uN = my[(s + 1) * PITCH + 1].x;
       double du = EXACT ? stencil_exact<MODEL>(a.k, t1, t3, c.x, uW, uE, uS, uN) : stencil_fast<MODEL>(a.k, t1, t3, c.x, uW, uE, uS, uN);
       double dv = 0.0;
       if (react_on) {
         react<MODEL, EXACT>(a.k, __ldg(a.brow + g1), c.x, c.y, du, dv);
-        const bool frozen = ((a.frz1 & 1) && g1 == 0) || ((a.frz1 & 2) && g1 == nyli - 1);
+        const bool frozen = ((a.frz1 & 1) && g1 == 0) || ((a.frz1 & 2) && g1 == nyli - 1) || ((a.frz1 & 4) && g1 == -1) || ((a.frz1 & 8) && g1 == nyli);
         du = frozen ? 0.0 : du;
         dv = frozen ? 0.0 : dv;
       }
@@ -152,8 +162,10 @@ __global__ void __launch_bounds__(256, MINB) rhs_pair_tile_kernel(const PairArgs
   }
 }
 
+// prepare_only: make sure the kernel is loaded and configured, launch nothing (a phi-split grid does this BEFORE it starts the
+// exchange: loading a module can wait for the device, and the neighbours' launches are already spinning on this rank's rows)
 template <int MODEL, bool EXACT, int MINB, int TY>
-int launch_pair_tile_shape(crd_grid *g, const PairArgs &a, cudaStream_t st) {
+int launch_pair_tile_shape(crd_grid *g, const PairArgs &a, cudaStream_t st, bool prepare_only) {
   const long long strips = (a.nx + kPairCols - 1) / kPairCols, tiles = strips * ((a.nyl + TY - 1) / TY);
   if (tiles > 2147483647LL) { set_error("slab too large for one launch"); return -1; }
   const size_t smem = (size_t)(TY + 4) * kPairPitch * 16 + 16;
@@ -165,6 +177,7 @@ int launch_pair_tile_shape(crd_grid *g, const PairArgs &a, cudaStream_t st) {
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
     attr_set[dev] = true;
   }
+  if (prepare_only) return 0;
   kern<<<(unsigned)tiles, 256, smem, st>>>(a);
   return check_launch(g->ctx, "rhs_pair_tile_kernel");
 }
@@ -172,21 +185,21 @@ int launch_pair_tile_shape(crd_grid *g, const PairArgs &a, cudaStream_t st) {
 // latency of its dependent FP64 chains: 8-row tiles fit four CTAs per SM at 64 registers, and 32 instead of 24 warps per SM are
 // worth more than the larger frame costs (2.67-3.16 against 3.21-3.67 ms at 16384^2; 10-row tiles: 2.73-3.2 ms).
 template <int MODEL, bool EXACT>
-int launch_pair_tile(crd_grid *g, const PairArgs &a, cudaStream_t st) {
-  if (EXACT) return launch_pair_tile_shape<MODEL, EXACT, 4, 8>(g, a, st);
-  return launch_pair_tile_shape<MODEL, EXACT, 3, kPairTY>(g, a, st);
+int launch_pair_tile(crd_grid *g, const PairArgs &a, cudaStream_t st, bool prepare_only) {
+  if (EXACT) return launch_pair_tile_shape<MODEL, EXACT, 4, 8>(g, a, st, prepare_only);
+  return launch_pair_tile_shape<MODEL, EXACT, 3, kPairTY>(g, a, st, prepare_only);
 }
 
 template <int MODEL, bool EXACT>
-int launch_pair_model(crd_grid *g, const PairArgs &a, cudaStream_t st) { return launch_pair_tile<MODEL, EXACT>(g, a, st); }
+int launch_pair_model(crd_grid *g, const PairArgs &a, cudaStream_t st, bool prepare_only) { return launch_pair_tile<MODEL, EXACT>(g, a, st, prepare_only); }
 
-int launch_pair(crd_grid *g, const PairArgs &a, cudaStream_t st) {
+int launch_pair(crd_grid *g, const PairArgs &a, cudaStream_t st, bool prepare_only = false) {
   const bool exact = g->p.arith == CRD_ARITH_EXACT;
   switch (g->p.model) {
-    case CRD_FHN_TORUS: return exact ? launch_pair_model<CRD_FHN_TORUS, true>(g, a, st) : launch_pair_model<CRD_FHN_TORUS, false>(g, a, st);
-    case CRD_GOLDBETER_TORUS: return exact ? launch_pair_model<CRD_GOLDBETER_TORUS, true>(g, a, st) : launch_pair_model<CRD_GOLDBETER_TORUS, false>(g, a, st);
-    case CRD_FHN_FLAT: return exact ? launch_pair_model<CRD_FHN_FLAT, true>(g, a, st) : launch_pair_model<CRD_FHN_FLAT, false>(g, a, st);
-    case CRD_GOLDBETER_FLAT: return exact ? launch_pair_model<CRD_GOLDBETER_FLAT, true>(g, a, st) : launch_pair_model<CRD_GOLDBETER_FLAT, false>(g, a, st);
+    case CRD_FHN_TORUS: return exact ? launch_pair_model<CRD_FHN_TORUS, true>(g, a, st, prepare_only) : launch_pair_model<CRD_FHN_TORUS, false>(g, a, st, prepare_only);
+    case CRD_GOLDBETER_TORUS: return exact ? launch_pair_model<CRD_GOLDBETER_TORUS, true>(g, a, st, prepare_only) : launch_pair_model<CRD_GOLDBETER_TORUS, false>(g, a, st, prepare_only);
+    case CRD_FHN_FLAT: return exact ? launch_pair_model<CRD_FHN_FLAT, true>(g, a, st, prepare_only) : launch_pair_model<CRD_FHN_FLAT, false>(g, a, st, prepare_only);
+    case CRD_GOLDBETER_FLAT: return exact ? launch_pair_model<CRD_GOLDBETER_FLAT, true>(g, a, st, prepare_only) : launch_pair_model<CRD_GOLDBETER_FLAT, false>(g, a, st, prepare_only);
   }
   set_error("unknown model %d", g->p.model);
   return -1;

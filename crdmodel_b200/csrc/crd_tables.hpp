@@ -11,7 +11,7 @@
 
 namespace {
 
-// needs g->p, g->nx, g->ny, g->js, g->nyl; fills the geometry members, g->k, cth[nx][2] and brow[nyl]
+// needs g->p, g->nx, g->ny, g->js, g->nyl; fills the geometry members, g->k, cth[nx][2] and brow[nyl + 2] (local rows at 1 .. nyl)
 inline void grid_host_tables(crd_grid *g, std::vector<double> &cth, std::vector<double> &brow) {
   const crd_params *p = &g->p;
   const bool torus = is_torus(p->model);
@@ -54,10 +54,14 @@ inline void grid_host_tables(crd_grid *g, std::vector<double> &cth, std::vector<
     }
   }
   // per-phi beta (:623-632); Goldbeter rows carry v0 + v1*b (:715)
-  brow.assign((size_t)g->nyl, 0.0);
+  // (one entry on either side for the rows of the neighbouring ranks, periodic in the global mesh: brow[0] is global row js - 1,
+  // brow[1 + j] local row j, brow[nyl + 1] global row je + 1 — the pass that forms two evaluations at once evaluates them)
+  brow.assign((size_t)g->nyl + 2, 0.0);
   const bool fhn = is_fhn(p->model);
-  for (long long j = 0; j < g->nyl; ++j) {
-    const double yy = g->ymin + (g->js + j) * (dy);
+  for (long long jj = -1; jj <= g->nyl; ++jj) {
+    const long long gj = ((g->js + jj) % g->ny + g->ny) % g->ny;
+    const long long j = jj + 1;
+    const double yy = g->ymin + (gj) * (dy);
     double b = p->beta;
     const bool vary = fhn ? (p->vary_beta != 0) : (p->vary_beta == 1);
     if (vary) b = p->beta_min + yy * (p->beta_max - p->beta_min) / (g->ymax - g->ymin);

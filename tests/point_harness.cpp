@@ -40,7 +40,7 @@ void sweep(const crd_grid &g, const std::vector<double> &cth, const std::vector<
                                        y[2 * (jS * nx + i)], y[2 * (jN * nx + i)]);
       double dv = 0.0;
       if (react_on) {
-        react<MODEL, true>(g.k, brow[j], uC, v, du, dv);
+        react<MODEL, true>(g.k, brow[j + 1], uC, v, du, dv);   // (brow[0] / brow[nyl + 1]: the neighbouring ranks' rows)
         if (frozen_now && (j == 0 || j == ny - 1)) { du = 0.0; dv = 0.0; }   // :643-653
       }
       ydot[2 * (j * nx + i)] = du;

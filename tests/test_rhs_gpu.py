@@ -541,3 +541,21 @@ def test_two_evaluations_in_one_pass(crd, ctx, model, arith, nx, ny):
     v = [small.new_vector() for _ in range(3)]
     assert small.f_pair(1.0, 1.1, c, *v) == 1
     small.close(); grid.close()
+
+
+@pytest.mark.parametrize("model,arith", [("fhn_torus", "exact"), ("gb_torus", "exact"), ("fhn_flat", "fast")])
+def test_two_evaluations_in_one_pass_on_a_phi_split(model, arith):
+    """crd_rhs_pair on connected grids (tests/pair_split_worker.py): the ranks, emulated on one GPU with a context and a stream
+    each, exchange TWO rows of y per side, then every rank forms F1 and F2 of its slab in one pass; gathered F1 and F2 are the
+    bits of the single-slab evaluations.  Runs in a process of its own with CUDA_MODULE_LOADING = EAGER and
+    CUDA_DEVICE_MAX_CONNECTIONS = 32, because the emulation has hazards that R ranks on R GPUs do not have: a rank's sequence is
+    push, wait, pass, all ranks are driven by ONE host thread, and (a) the first launch of a kernel loads it lazily, which waits
+    for the device — where another rank's wait kernel is spinning on rows this thread has not pushed yet; (b) with the default 8
+    hardware queues two ranks' streams can share one, and one rank's push then queues up behind the other's pass, which waits for
+    exactly that push."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", CUDA_MODULE_LOADING="EAGER")
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pair_split_worker.py"), model, arith],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "PAIR SPLIT OK" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
