@@ -712,8 +712,8 @@ def main():
         solver.free()
         g.fill_synthetic(y)
         att = max(1, n1["nst_attempts"] - n0["nst_attempts"])
-        # one slab (FHN in either arithmetic): f(tn, ynew) and the next step's second stage are one pass (crd_rhs_pair): 240 B per point
-        bpp = 240 if not use_dist else 272
+        # f(tn, ynew) and the next step's second stage are one pass (crd_rhs_pair): 240 B per point
+        bpp = 240
         return {"steps_per_s": (n1["nst"] - n0["nst"]) / dt_n, "step_attempts_per_s": att / dt_n, "ms_per_attempt": 1e3 * dt_n / att,
                 "nst": n1["nst"] - n0["nst"], "nfe": n1["nfe"] - n0["nfe"], "netf": n1["netf"] - n0["netf"],
                 "rhs_per_attempt": (n1["nfe"] - n0["nfe"]) / att, "flag": flag_n, "mode": "ARK_NORMAL, 50-step limit (flag -1 = the limit, as intended)",
