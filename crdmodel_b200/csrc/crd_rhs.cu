@@ -319,7 +319,9 @@ int crd_rhs_lincomb_finish(crd_grid *g, double t, int s, const double *c, const 
   if (!g || !c || !hb || !hd || !X_dev || !ynew_dev || !out) { set_error("crd_rhs_lincomb_finish: null argument"); return -1; }
   // decided before anything is posted to the neighbours: 5 stages, a mesh the streaming kernel is made for, non-zero solution
   // weights of the stored stages (the kernel adds those terms unconditionally; the op-by-op chain skips zero weights)
-  if (s != kMaxLc || g->nx < 192 || g->nx * g->nyl < (1LL << 20)) return 1;
+  // (on a phi-split grid the size test uses the smallest slab of the split, so that every rank comes to the same answer)
+  const long long rows_min = g->connected ? g->ny / (g->ctx->nranks > 1 ? g->ctx->nranks : 1) : g->nyl;
+  if (s != kMaxLc || g->nx < 192 || g->nx * rows_min < (1LL << 20)) return 1;
   for (int j = 0; j + 1 < s; ++j)
     if (hb[j] == 0.0) return 1;
   crd_ctx *ctx = g->ctx;
@@ -370,7 +372,15 @@ int crd_f_lincomb_finish(realtype t, int s, const realtype *c, const realtype *h
 // neighbours first exchange two rows of y per side (one exchange for both evaluations).
 int crd_rhs_pair(crd_grid *g, double t1, double t2, double c, const double *y, double *f1, double *f2) {
   if (!g || !y || !f1 || !f2) { set_error("crd_rhs_pair: null argument"); return -1; }
-  if (g->nx < kPairCols || g->nyl < 32 || g->nx * g->nyl < (1LL << 20) || g->variant != 0) return 1;
+  // Does it apply?  On a phi-split grid every rank must come to the same answer (the pass makes ONE exchange where the two
+  // evaluations make two: ranks that disagreed would wait for rows that never come), so the size test there uses nothing but
+  // the global mesh and the number of ranks — the smallest slab of the split, whatever this rank's own share is.
+  long long rows = g->nyl;
+  if (g->connected) {
+    const long long R = g->ctx->nranks > 1 ? g->ctx->nranks : 1;
+    rows = g->ny / R;
+  }
+  if (g->nx < kPairCols || rows < 32 || g->nyl < 2 || g->nx * rows < (1LL << 20) || g->variant != 0) return 1;
   if (y == f1 || y == f2 || f1 == f2) { set_error("crd_rhs_pair: aliased vectors"); return -1; }
   if (use(g->ctx)) return -1;
   if (g->connected && g->epoch != g->computed) { set_error("crd_rhs_pair: previous epoch was posted but never computed"); return -1; }

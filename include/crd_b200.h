@@ -176,8 +176,9 @@ int crd_f_lincomb_finish(realtype t, int s, const realtype *c, const realtype *h
  * whose state needs nothing but y and f1 (src/FHNmodel_torus.cpp:423: two of the f() calls inside ARKode()).  y is read once,
  * y + c f1 never exists in memory: 48 instead of 80 B per point.  f1 and f2 have the bits of crd_rhs followed by
  * crd_rhs_lincomb(2, (1, c), (y, f1)).  On a phi-split grid the ranks exchange two rows of y per side first (one exchange for
- * both evaluations; every rank must make the call).  Returns 0, or 1 when it does not apply (a slab too small to stream, a forced
- * kernel variant): issue the two evaluations separately. */
+ * both evaluations; every rank must make the call, and every rank gets the same answer: the size test uses the global mesh and
+ * the number of ranks).  Returns 0, or 1 when it does not apply (slabs too small to stream, a forced kernel variant): issue the
+ * two evaluations separately. */
 int crd_rhs_pair(crd_grid *g, double t1, double t2, double c, const double *y_dev, double *f1_dev, double *f2_dev);
 /* the integrator's form (crd_fused_ops.rhs_pair); also declines (1) where the pass is not faster than the two launches:
  * CRD_ARITH_EXACT grids of the Goldbeter programs (bound by FP64 work) */
