@@ -67,3 +67,16 @@ extern "C" int point_harness_rhs(const crd_params *p, double t, int react_on, co
   }
   return -1;
 }
+
+// the per-phi beta table of one rank of a phi split (js .. je of ny rows): out[0] = the row south of the slab, out[1 + j] = local
+// row j, out[nyl + 1] = the row north of it (periodic in the global mesh)
+extern "C" int point_harness_brow(const crd_params *p, double *out) {
+  crd_grid g;
+  g.p = *p;
+  g.nx = p->nx; g.ny = p->ny; g.js = p->js; g.je = p->je; g.nyl = p->je - p->js + 1;
+  std::vector<double> cth, brow;
+  grid_host_tables(&g, cth, brow);
+  std::copy(brow.begin(), brow.end(), out);
+  return (int)brow.size();
+}
+

@@ -131,3 +131,29 @@ def test_device_point_source_at_baseline_meshes(harness, oracle):
             sc = scale_of(P, y)
             for i, hx in c["samples"].items():
                 assert abs(got[int(i)] - float.fromhex(hx)) <= 4e-16 * sc[int(i)], (c["name"], i)
+
+
+def test_beta_table_of_a_phi_split_carries_the_neighbours_rows(harness):
+    """grid_host_tables of a rank of a phi split: brow[1 + j] is local row j, brow[0] / brow[nyl + 1] the rows just south / north of
+    the slab in the periodic global mesh — the very values the owning ranks hold for them (the pass that forms two evaluations at
+    once evaluates f on those rows, src/FHNmodel_torus.cpp:623,631: beta(phi) from the GLOBAL row index)."""
+    import crdmodel_b200.api as api
+    harness.point_harness_brow.restype = C.c_int
+    harness.point_harness_brow.argtypes = [C.c_void_p, C.c_void_p]
+    for model in ("fhn_torus", "gb_flat", "gb_torus"):
+        nx, ny = 40, 101
+        whole = np.zeros(ny + 2)
+        P = api.make_params(model, nx, ny, vary_beta=1)
+        assert harness.point_harness_brow(C.byref(P), whole.ctypes.data) == ny + 2
+        assert whole[0] == whole[ny] and whole[ny + 1] == whole[1]            # one slab: its own last / first row
+        if model != "gb_torus":                                                # (the Goldbeter torus program ignores varyBeta = 1)
+            assert len(set(whole[1:ny + 1])) == ny                             # beta really varies with phi
+        for nr in (2, 3, 7):
+            for r in range(nr):
+                js, je = ny * r // nr, ny * (r + 1) // nr - 1
+                nyl = je - js + 1
+                part = np.zeros(nyl + 2)
+                Pr = api.make_params(model, nx, ny, js=js, je=je, vary_beta=1)
+                assert harness.point_harness_brow(C.byref(Pr), part.ctypes.data) == nyl + 2
+                assert part[1:nyl + 1].tobytes() == whole[1 + js:2 + je].tobytes()
+                assert part[0] == whole[1 + (js - 1) % ny] and part[nyl + 1] == whole[1 + (je + 1) % ny]
