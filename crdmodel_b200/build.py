@@ -23,7 +23,7 @@ LIB_ARK = os.path.join(LIB_DIR, "libcrd_ark.so")
 
 CUDA_SOURCES = ["csrc/crd_ctx.cu", "csrc/crd_rhs.cu", "csrc/crd_nvector.cu", "csrc/crd_resident.cu", "csrc/crd_snapshot.cu"]
 HOST_SOURCES = ["host/crd_ark.cpp", "host/crd_nvector_generic.c"]
-HEADERS = ["csrc/crd_common.cuh", "csrc/crd_grid.cuh", "csrc/crd_rhs_kernels.cuh", "csrc/crd_rhs_point.cuh", "csrc/crd_fused.cuh", "csrc/crd_tables.hpp", "../include/crd_b200.h",
+HEADERS = ["csrc/crd_common.cuh", "csrc/crd_grid.cuh", "csrc/crd_rhs_kernels.cuh", "csrc/crd_rhs_pair.cuh", "csrc/crd_rhs_point.cuh", "csrc/crd_fused.cuh", "csrc/crd_tables.hpp", "../include/crd_b200.h",
            "host/crd_pow.h", "../include/crd_ark.h", "../include/crd_sundials_compat.h"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "--threads", "4", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "-Xlinker", "-Bsymbolic", "-shared"]
