@@ -39,3 +39,30 @@ def test_stdout_is_exactly_the_json_line_even_when_libraries_write_to_fd_1():
     assert r.returncode == 0
     assert r.stdout == '{"metric": "m", "value": 1}\n'
     assert "NCCL version" in r.stderr and "noise" in r.stderr
+
+
+def test_committed_gpu_lines_carry_the_contract():
+    """The GPU arm's lines kept under profiles/ (written by bench.py on B200 boxes this round): contract keys, the roofline
+    arithmetic, parity of the timed result against the reference's f(), a launch count, clocks without a thermal / hardware flag."""
+    full = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+            "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "parity", "sustained")
+    for name, n in (("r02_bench_n1_final3.json", 1), ("r02_bench_n1_final4.json", 1), ("r02_bench_n2_final2.json", 2),
+                    ("r02_bench_n4_final2.json", 4), ("r02_bench_n8_final2.json", 8)):
+        d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
+        for k in full:
+            assert k in d, (name, k)
+        assert d["n_gpus"] == n and d["dtype"] == "f64" and d["higher_is_better"] is True and d["vs_baseline"] is None
+        pts = d["roofline"]["points_per_launch"]
+        assert abs(d["value"] - n * pts / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and abs(r["achieved"] - 32 * pts / (d["ms_per_step"] * 1e-3) / 1e9) <= 1e-6 * r["achieved"]
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.7 < r["frac"] < 1.2
+        assert d["parity"]["bitwise"] is True and d["parity"]["rows_checked"] == 40 * n and d["parity"]["ranks"] == n
+        assert d["gpu_launches"] == d["steps"]                       # one launch per evaluation, at every N
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        assert d["e2e"]["h2d_bytes_per_step"] == 16 * pts and d["e2e"]["matches_device_result"] is True
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_n1_final3.json")).read().strip().splitlines()[-1])
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] > 0
+    fp = [json.loads(open(os.path.join(ROOT, "profiles", f)).read().strip().splitlines()[-1])["integrator_fingerprint"]
+          for f in ("r02_bench_n1_final4.json", "r02_bench_n2_final2.json", "r02_bench_n4_final2.json")]
+    assert all(f["sum64"] == fp[0]["sum64"] and f["xor64"] == fp[0]["xor64"] and f["t"] == fp[0]["t"] for f in fp)
